@@ -1,0 +1,147 @@
+"""TEST INFRASTRUCTURE — ctypes wrapper of the CPU oracle (oracle/ctf_oracle.c).
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU-baseline legs may
+import this.  The product path (marl_ctf_development_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from marl_ctf_development_b200.config import N_METRICS, CompiledEnv, CtfConfig, compile_config
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libctf_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "ctf_oracle.c")
+    hdr = os.path.join(_HERE, "..", "include", "ctf_b200.h")
+    stale = (
+        force
+        or not os.path.exists(_LIB_PATH)
+        or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH))
+        or (os.path.exists(hdr) and os.path.getmtime(hdr) > os.path.getmtime(_LIB_PATH))
+    )
+    if stale:
+        subprocess.run(["make", "-s", "-C", _HERE] + (["-B"] if force else []), check=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.ctf_oracle_env_size.restype = C.c_size_t
+        L.ctf_oracle_init.argtypes = [C.c_void_p, C.POINTER(CtfConfig), C.c_uint64, C.c_uint32]
+        L.ctf_oracle_reset.argtypes = [C.c_void_p]
+        L.ctf_oracle_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ctf_oracle_observe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ctf_oracle_standardise_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ctf_oracle_metadata.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ctf_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        L.ctf_oracle_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.ctf_oracle_f64_to_f16_to_f32.argtypes = [C.c_double]
+        L.ctf_oracle_f64_to_f16_to_f32.restype = C.c_float
+        L.ctf_oracle_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ctf_oracle_run_baseline.argtypes = [C.POINTER(CtfConfig), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int]
+        L.ctf_oracle_run_baseline.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleEnv:
+    """One sequential env with the reference's semantics; ``compiled`` from config.compile_config."""
+
+    def __init__(self, compiled: CompiledEnv | None = None, seed: int = 0, env_id: int = 0, **env_config):
+        self.ce = compiled if compiled is not None else compile_config(**env_config)
+        self.L = lib()
+        self._buf = C.create_string_buffer(self.L.ctf_oracle_env_size())
+        self._e = C.cast(self._buf, C.c_void_p)
+        self.N = self.ce.N_AGENTS
+        self.G = self.ce.GRID_SIZE
+        self.Cn = self.ce.n_channels
+        self.M = 6 + 2 * self.N
+        self.L.ctf_oracle_init(self._e, C.byref(self.ce.cfg), seed, env_id)
+
+    def reset(self):
+        self.L.ctf_oracle_reset(self._e)
+
+    def step(self, actions):
+        a = np.ascontiguousarray(np.asarray(actions, dtype=np.uint8))
+        assert a.shape == (self.N,)
+        r = np.zeros(self.N, dtype=np.float32)
+        d = np.zeros(1, dtype=np.uint8)
+        self.L.ctf_oracle_step(self._e, _p(a), _p(r), _p(d))
+        return r, bool(d[0])
+
+    def observe(self, reverse_flags=None, u8=False):
+        obs = np.zeros((self.N, self.Cn, self.G, self.G), dtype=np.uint8 if u8 else np.float32)
+        meta = np.zeros((self.N, self.M), dtype=np.float32)
+        rf = None if reverse_flags is None else np.ascontiguousarray(np.asarray(reverse_flags, dtype=np.uint8))
+        self.L.ctf_oracle_observe(
+            self._e, None if rf is None else _p(rf), None if u8 else _p(obs), _p(obs) if u8 else None, _p(meta)
+        )
+        return obs, meta
+
+    def standardise_state(self, agent_idx, reverse_grid=False):
+        out = np.zeros((1, self.Cn, self.G, self.G), dtype=np.uint8)
+        self.L.ctf_oracle_standardise_state(self._e, int(agent_idx), int(bool(reverse_grid)), _p(out))
+        return out
+
+    def get_env_metadata(self, agent_idx):
+        out = np.zeros((1, self.M), dtype=np.float32)
+        self.L.ctf_oracle_metadata(self._e, int(agent_idx), _p(out))
+        return out
+
+    def state(self) -> dict:
+        n, g = self.N, self.G
+        grid = np.zeros((g, g), dtype=np.uint8)
+        pos = np.zeros((n, 2), dtype=np.int32)
+        hp = np.zeros(n, dtype=np.int32)
+        flag = np.zeros(n, dtype=np.uint8)
+        inv = np.zeros(n, dtype=np.int32)
+        sc = np.zeros(5, dtype=np.int32)
+        stats = np.zeros((N_METRICS, n), dtype=np.uint32)
+        visits = np.zeros((n, g, g), dtype=np.uint8)
+        self.L.ctf_oracle_get_state(self._e, _p(grid), _p(pos), _p(hp), _p(flag), _p(inv), _p(sc), _p(stats), _p(visits))
+        return {
+            "grid": grid,
+            "pos": pos.astype(np.uint8),
+            "hp_q": hp,
+            "has_flag": flag,
+            "inventory": inv,
+            "step": int(sc[0]),
+            "episode": int(sc[1]),
+            "captures": sc[2:4].astype(np.int64),
+            "done": bool(sc[4]),
+            "stats": stats.astype(np.int64),
+            "visits": visits,
+        }
+
+    def set_state(self, grid, pos, hp_q, has_flag, inventory, step, episode, captures, done=False):
+        grid = np.ascontiguousarray(np.asarray(grid, dtype=np.uint8))
+        pos = np.ascontiguousarray(np.asarray(pos, dtype=np.int32))
+        hp = np.ascontiguousarray(np.asarray(hp_q, dtype=np.int32))
+        flag = np.ascontiguousarray(np.asarray(has_flag, dtype=np.uint8))
+        inv = np.ascontiguousarray(np.asarray(inventory, dtype=np.int32))
+        sc = np.array([step, episode, captures[0], captures[1], int(done)], dtype=np.int32)
+        self.L.ctf_oracle_set_state(self._e, _p(grid), _p(pos), _p(hp), _p(flag), _p(inv), _p(sc))
+
+
+def run_baseline(compiled: CompiledEnv, n_envs: int, steps: int, seed: int, with_obs: bool, n_threads: int) -> float:
+    """Multi-threaded CPU run of the oracle (bench.py cpu_baseline / --impl reference). Returns a checksum."""
+    return float(lib().ctf_oracle_run_baseline(C.byref(compiled.cfg), n_envs, steps, seed, int(with_obs), n_threads))
+
+
+def f64_to_f16_to_f32(x: float) -> float:
+    return float(lib().ctf_oracle_f64_to_f16_to_f32(float(x)))
