@@ -1,0 +1,103 @@
+"""Pins the CPU oracle against the imported, unmodified reference with injected draws.
+
+Runs only where /root/reference exists (this container); the GPU box relies on the
+committed traces in tests/golden/ instead.
+"""
+import numpy as np
+import pytest
+
+import traces
+from helpers import STATE_KEYS, assert_state_equal, bits
+from marl_ctf_development_b200.config import compile_config, env_dims
+from oracle import ref_shim as rs
+from oracle.ctf_oracle import OracleEnv
+
+pytestmark = [
+    pytest.mark.reference,
+    pytest.mark.skipif(not rs.available(), reason="reference tree not present"),
+    pytest.mark.filterwarnings("ignore"),
+]
+
+CASES = [
+    ("0_the_split", "seek", 260),
+    ("1_fence", "builder", 200),
+    ("2_jailbreak", "seek", 260),
+    ("3_one_way_out", "builder", 200),
+    ("4_keyhole", "seek", 200),
+    ("5_skittles", "builder", 200),
+    ("6_the_wall", "seek", 200),
+    ("7_gridlocked", "builder", 503),
+    ("8_arena", "seek", 503),
+    ("8_arena", "uniform", 200),
+]
+
+
+@pytest.mark.parametrize("exp,kind,steps", CASES, ids=[f"{e}-{k}" for e, k, _ in CASES])
+def test_oracle_equals_reference_step_by_step(exp, kind, steps):
+    ec = rs.experiment_env_config(exp)
+    ce = compile_config(**ec)
+    seed, env_id = 99, 1234
+    ref = rs.make_injected_env(ec, seed=seed, env_id=env_id)
+    orc = OracleEnv(ce, seed=seed, env_id=env_id)
+    assert env_dims(ce) == ref.get_env_dims()
+    assert [int(t) for t in ce.TILES_USED] == [int(t) for t in ref.TILES_USED]
+    pol = traces.make_policy(kind, ce)
+    rng = np.random.default_rng(5)
+    for episode in range(2):
+        if episode:
+            ref.reset()
+            orc.reset()
+        for t in range(steps if episode == 0 else 30):
+            s = rs.snapshot(ref, ce.cfg.hp_scale)
+            a = pol(rng, s["pos"], s["has_flag"])
+            _, rr, rd = ref.step(a.tolist())
+            orr, od = orc.step(a)
+            assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"{exp}/{kind} ep{episode} t={t}")
+            assert rd == od
+            assert np.array_equal(bits(np.array(rr, dtype=np.float32)), bits(orr))
+            if t % 5 == 0:
+                ro, rm = rs.observations(ref)
+                oo, om = orc.observe()
+                assert np.array_equal(ro, oo)
+                assert np.array_equal(bits(rm), bits(om))
+        st = orc.state()
+        assert np.array_equal(rs.agent_metrics(ref), st["stats"])
+        vm = np.stack([ref.metrics["agent_visitation_maps"][i] for i in range(ce.N_AGENTS)])
+        assert np.array_equal(vm, st["visits"])
+
+
+def test_arbitrary_reverse_flags_and_symmetry_assert():
+    """standardise_state(i, reverse_grid) for both flag values; the ctor's symmetry assert (gridworld_ctf.py:476-477)."""
+    ec = rs.experiment_env_config("8_arena")
+    ce = compile_config(**ec)
+    ref = rs.make_injected_env(ec, seed=1, env_id=1)
+    orc = OracleEnv(ce, seed=1, env_id=1)
+    assert np.array_equal(orc.standardise_state(0), orc.standardise_state(1, reverse_grid=True))
+    rng = np.random.default_rng(0)
+    for t in range(60):
+        a = traces.uniform_actions(rng, ce.N_AGENTS)
+        ref.step(a.tolist())
+        orc.step(a)
+    for i in range(ce.N_AGENTS):
+        for rev in (False, True):
+            assert np.array_equal(ref.standardise_state(i, reverse_grid=rev), orc.standardise_state(i, reverse_grid=rev))
+
+
+@pytest.mark.parametrize("exp,flip", [("0_the_split", 2), ("1_fence", 0), ("8_arena", None), ("7_gridlocked", 1)])
+def test_all_flip_axes_are_covered(exp, flip):
+    """FLIP_AXIS 2, 0 and None appear in shipped scenarios; 1 is forced onto a map to cover np.flip(axis=1)."""
+    ec = rs.experiment_env_config(exp)
+    ec["SCENARIO"] = dict(ec["SCENARIO"], FLIP_AXIS=flip)
+    ec["MAP_SYMMETRY_CHECK"] = False
+    ce = compile_config(**ec)
+    ref = rs.make_injected_env(ec, seed=3, env_id=3)
+    orc = OracleEnv(ce, seed=3, env_id=3)
+    rng = np.random.default_rng(1)
+    for t in range(25):
+        a = traces.uniform_actions(rng, ce.N_AGENTS)
+        ref.step(a.tolist())
+        orc.step(a)
+    for i in range(ce.N_AGENTS):
+        assert np.array_equal(ref.standardise_state(i, reverse_grid=True), orc.standardise_state(i, reverse_grid=True))
+    for a in range(9):
+        assert ref.get_reversed_action(a) == ce.cfg.reversed_action[a]

@@ -53,3 +53,11 @@ def make_policy(kind: str, ce):
     if kind == "builder":
         return lambda rng, pos, has_flag: seek_actions(rng, ce, pos, has_flag, eps=0.5, second_p=0.6)
     raise ValueError(kind)
+
+
+OBS_EVERY = 20
+
+
+def snap_after_step(t: int, env_step: int, game_steps: int) -> bool:
+    """Whether the golden traces hold an observation after recorded step t (t counts from 1)."""
+    return t % OBS_EVERY == 0 or env_step in (game_steps - 1, game_steps, game_steps + 1)
