@@ -542,3 +542,124 @@ double ctf_oracle_run_baseline(const ctf_config_t* cfg, int n_envs, int steps, u
     pthread_mutex_destroy(&job.lock);
     return job.checksum;
 }
+
+/* ------------------------------------------------------------------ batch API for the parity tests
+ * B sequential envs with global ids env_id_base + b; the same entry points as the single-env API,
+ * looped (optionally over threads) so that Python does one call per step. */
+typedef struct ctf_oracle_batch {
+    ctf_config_t cfg;
+    int B;
+    ctf_oracle_env_t* envs;
+} ctf_oracle_batch_t;
+
+ctf_oracle_batch_t* ctf_oracle_batch_create(const ctf_config_t* cfg, int B, uint64_t seed, uint32_t env_id_base) {
+    ctf_oracle_batch_t* bt = (ctf_oracle_batch_t*)malloc(sizeof(ctf_oracle_batch_t));
+    bt->cfg = *cfg;
+    bt->B = B;
+    bt->envs = (ctf_oracle_env_t*)malloc(sizeof(ctf_oracle_env_t) * (size_t)B);
+    for (int b = 0; b < B; ++b) ctf_oracle_init(&bt->envs[b], &bt->cfg, seed, env_id_base + (uint32_t)b);
+    return bt;
+}
+
+void ctf_oracle_batch_destroy(ctf_oracle_batch_t* bt) {
+    if (!bt) return;
+    free(bt->envs);
+    free(bt);
+}
+
+void ctf_oracle_batch_reset(ctf_oracle_batch_t* bt) {
+    for (int b = 0; b < bt->B; ++b) ctf_oracle_reset(&bt->envs[b]);
+}
+
+void ctf_oracle_batch_step(ctf_oracle_batch_t* bt, const uint8_t* actions, float* rewards, uint8_t* dones) {
+    const int N = bt->cfg.n_agents;
+    for (int b = 0; b < bt->B; ++b) ctf_oracle_step(&bt->envs[b], actions + (size_t)b * N, rewards + (size_t)b * N, dones + b);
+}
+
+void ctf_oracle_batch_observe(const ctf_oracle_batch_t* bt, const uint8_t* reverse_flags, float* obs, uint8_t* obs_u8, float* meta) {
+    const ctf_config_t* c = &bt->cfg;
+    const size_t E = (size_t)c->n_agents * c->n_channels * c->grid_size * c->grid_size;
+    const size_t NM = (size_t)c->n_agents * (6 + 2 * c->n_agents);
+    for (int b = 0; b < bt->B; ++b)
+        ctf_oracle_observe(&bt->envs[b], reverse_flags, obs ? obs + b * E : NULL, obs_u8 ? obs_u8 + b * E : NULL,
+                           meta ? meta + b * NM : NULL);
+}
+
+void ctf_oracle_batch_get_state(const ctf_oracle_batch_t* bt, uint8_t* grid, int32_t* pos, int32_t* hp_q, uint8_t* has_flag,
+                                int32_t* inventory, int32_t* scalars, uint32_t* stats, uint8_t* visits) {
+    const ctf_config_t* c = &bt->cfg;
+    const size_t GG = (size_t)c->grid_size * c->grid_size, N = (size_t)c->n_agents;
+    for (int b = 0; b < bt->B; ++b)
+        ctf_oracle_get_state(&bt->envs[b], grid ? grid + b * GG : NULL, pos ? pos + b * N * 2 : NULL, hp_q ? hp_q + b * N : NULL,
+                             has_flag ? has_flag + b * N : NULL, inventory ? inventory + b * N : NULL,
+                             scalars ? scalars + b * 5 : NULL, stats ? stats + b * CTF_N_METRICS * N : NULL,
+                             visits ? visits + b * N * GG : NULL);
+}
+
+void ctf_oracle_batch_set_state(ctf_oracle_batch_t* bt, const uint8_t* grid, const int32_t* pos, const int32_t* hp_q,
+                                const uint8_t* has_flag, const int32_t* inventory, const int32_t* scalars) {
+    const ctf_config_t* c = &bt->cfg;
+    const size_t GG = (size_t)c->grid_size * c->grid_size, N = (size_t)c->n_agents;
+    for (int b = 0; b < bt->B; ++b)
+        ctf_oracle_set_state(&bt->envs[b], grid + b * GG, pos + b * N * 2, hp_q + b * N, has_flag + b * N, inventory + b * N,
+                             scalars + b * 5);
+}
+
+/* Threaded continuation of a persistent batch (bench.py CPU legs): every env advances `steps` steps from
+ * its current state with uniform random actions, the callers' per-step work included when with_obs
+ * (observations + metadata for every agent, then step), auto-reset after done.  Thread i owns a
+ * contiguous slice of envs. */
+typedef struct batch_run_job {
+    ctf_oracle_batch_t* bt;
+    int lo, hi, steps, with_obs;
+    uint64_t seed;
+    double checksum;
+} batch_run_job_t;
+
+static void* batch_run_worker(void* arg) {
+    batch_run_job_t* job = (batch_run_job_t*)arg;
+    const ctf_config_t* cfg = &job->bt->cfg;
+    const int N = cfg->n_agents;
+    const size_t per_env_obs = (size_t)N * cfg->n_channels * cfg->grid_size * cfg->grid_size;
+    float* obs = (float*)malloc(per_env_obs * sizeof(float));
+    float* meta = (float*)malloc((size_t)N * (6 + 2 * N) * sizeof(float));
+    double checksum = 0.0;
+    for (int b = job->lo; b < job->hi; ++b) {
+        ctf_oracle_env_t* e = &job->bt->envs[b];
+        uint64_t s = job->seed * 0x9E3779B97F4A7C15ull + ((uint64_t)b << 20) + (uint64_t)e->step + ((uint64_t)e->episode << 40);
+        uint8_t actions[CTF_MAX_AGENTS];
+        float rewards[CTF_MAX_AGENTS];
+        uint8_t done = (uint8_t)e->done;
+        for (int t = 0; t < job->steps; ++t) {
+            if (done) ctf_oracle_reset(e);
+            if (job->with_obs) {
+                ctf_oracle_observe(e, NULL, obs, NULL, meta);
+                checksum += obs[(size_t)(t * 7919) % per_env_obs] + meta[0];
+            }
+            uint64_t r = splitmix64(&s);
+            for (int i = 0; i < N; ++i) { actions[i] = (uint8_t)(((r & 0xFF) * 9) >> 8); r >>= 8; }
+            ctf_oracle_step(e, actions, rewards, &done);
+            checksum += rewards[0];
+        }
+    }
+    free(obs); free(meta);
+    job->checksum = checksum;
+    return NULL;
+}
+
+double ctf_oracle_batch_run(ctf_oracle_batch_t* bt, int steps, uint64_t seed, int with_obs, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > bt->B) n_threads = bt->B;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    batch_run_job_t* jobs = (batch_run_job_t*)malloc(sizeof(batch_run_job_t) * (size_t)n_threads);
+    double checksum = 0.0;
+    for (int i = 0; i < n_threads; ++i) {
+        jobs[i].bt = bt; jobs[i].steps = steps; jobs[i].with_obs = with_obs; jobs[i].seed = seed; jobs[i].checksum = 0.0;
+        jobs[i].lo = (int)((long long)bt->B * i / n_threads);
+        jobs[i].hi = (int)((long long)bt->B * (i + 1) / n_threads);
+        pthread_create(&th[i], NULL, batch_run_worker, &jobs[i]);
+    }
+    for (int i = 0; i < n_threads; ++i) { pthread_join(th[i], NULL); checksum += jobs[i].checksum; }
+    free(th); free(jobs);
+    return checksum;
+}

@@ -51,6 +51,16 @@ def lib():
         L.ctf_oracle_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ctf_oracle_run_baseline.argtypes = [C.POINTER(CtfConfig), C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int]
         L.ctf_oracle_run_baseline.restype = C.c_double
+        L.ctf_oracle_batch_create.argtypes = [C.POINTER(CtfConfig), C.c_int, C.c_uint64, C.c_uint32]
+        L.ctf_oracle_batch_create.restype = C.c_void_p
+        L.ctf_oracle_batch_destroy.argtypes = [C.c_void_p]
+        L.ctf_oracle_batch_reset.argtypes = [C.c_void_p]
+        L.ctf_oracle_batch_step.argtypes = [C.c_void_p] * 4
+        L.ctf_oracle_batch_observe.argtypes = [C.c_void_p] * 5
+        L.ctf_oracle_batch_get_state.argtypes = [C.c_void_p] * 9
+        L.ctf_oracle_batch_set_state.argtypes = [C.c_void_p] * 7
+        L.ctf_oracle_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int]
+        L.ctf_oracle_batch_run.restype = C.c_double
         _lib = L
     return _lib
 
@@ -136,6 +146,86 @@ class OracleEnv:
         inv = np.ascontiguousarray(np.asarray(inventory, dtype=np.int32))
         sc = np.array([step, episode, captures[0], captures[1], int(done)], dtype=np.int32)
         self.L.ctf_oracle_set_state(self._e, _p(grid), _p(pos), _p(hp), _p(flag), _p(inv), _p(sc))
+
+
+class OracleBatch:
+    """B sequential oracle envs with global ids env_id_base + b (mirrors GridworldCtfGPU's batch semantics)."""
+
+    def __init__(self, compiled: CompiledEnv, num_envs: int, seed: int = 0, env_id_base: int = 0):
+        self.ce = compiled
+        self.L = lib()
+        self.B = int(num_envs)
+        self.N, self.G, self.Cn = compiled.N_AGENTS, compiled.GRID_SIZE, compiled.n_channels
+        self.M = 6 + 2 * self.N
+        self._h = C.c_void_p(self.L.ctf_oracle_batch_create(C.byref(compiled.cfg), self.B, seed, env_id_base))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ctf_oracle_batch_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        self.L.ctf_oracle_batch_reset(self._h)
+
+    def step(self, actions):
+        a = np.ascontiguousarray(np.asarray(actions, dtype=np.uint8))
+        assert a.shape == (self.B, self.N)
+        r = np.zeros((self.B, self.N), dtype=np.float32)
+        d = np.zeros(self.B, dtype=np.uint8)
+        self.L.ctf_oracle_batch_step(self._h, _p(a), _p(r), _p(d))
+        return r, d
+
+    def observe(self, reverse_flags=None, u8=False):
+        obs = np.zeros((self.B, self.N, self.Cn, self.G, self.G), dtype=np.uint8 if u8 else np.float32)
+        meta = np.zeros((self.B, self.N, self.M), dtype=np.float32)
+        rf = None if reverse_flags is None else np.ascontiguousarray(np.asarray(reverse_flags, dtype=np.uint8))
+        self.L.ctf_oracle_batch_observe(
+            self._h, None if rf is None else _p(rf), None if u8 else _p(obs), _p(obs) if u8 else None, _p(meta)
+        )
+        return obs, meta
+
+    def run(self, steps: int, seed: int, with_obs: bool, n_threads: int) -> float:
+        """Threaded continuation with uniform random actions (CPU legs of bench.py). Returns a checksum."""
+        return float(self.L.ctf_oracle_batch_run(self._h, int(steps), int(seed), int(with_obs), int(n_threads)))
+
+    def state(self) -> dict:
+        B, n, g = self.B, self.N, self.G
+        grid = np.zeros((B, g, g), dtype=np.uint8)
+        pos = np.zeros((B, n, 2), dtype=np.int32)
+        hp = np.zeros((B, n), dtype=np.int32)
+        flag = np.zeros((B, n), dtype=np.uint8)
+        inv = np.zeros((B, n), dtype=np.int32)
+        sc = np.zeros((B, 5), dtype=np.int32)
+        stats = np.zeros((B, N_METRICS, n), dtype=np.uint32)
+        visits = np.zeros((B, n, g, g), dtype=np.uint8)
+        self.L.ctf_oracle_batch_get_state(self._h, _p(grid), _p(pos), _p(hp), _p(flag), _p(inv), _p(sc), _p(stats), _p(visits))
+        return {
+            "grid": grid,
+            "pos": pos.astype(np.uint8),
+            "hp_q": hp,
+            "has_flag": flag,
+            "inventory": inv,
+            "step": sc[:, 0].astype(np.int64),
+            "episode": sc[:, 1].astype(np.int64),
+            "captures": sc[:, 2:4].astype(np.int64),
+            "done": sc[:, 4].astype(bool),
+            "stats": stats.astype(np.int64),
+            "visits": visits,
+        }
+
+    def set_state(self, grid, pos, hp_q, has_flag, inventory, step, episode, captures):
+        B = self.B
+        grid = np.ascontiguousarray(np.asarray(grid, dtype=np.uint8))
+        pos = np.ascontiguousarray(np.asarray(pos, dtype=np.int32))
+        hp = np.ascontiguousarray(np.asarray(hp_q, dtype=np.int32))
+        flag = np.ascontiguousarray(np.asarray(has_flag, dtype=np.uint8))
+        inv = np.ascontiguousarray(np.asarray(inventory, dtype=np.int32))
+        sc = np.zeros((B, 5), dtype=np.int32)
+        sc[:, 0] = np.asarray(step).reshape(B)
+        sc[:, 1] = np.asarray(episode).reshape(B)
+        sc[:, 2:4] = np.asarray(captures).reshape(B, 2)
+        sc[:, 4] = sc[:, 0] >= self.ce.GAME_STEPS
+        self.L.ctf_oracle_batch_set_state(self._h, _p(grid), _p(pos), _p(hp), _p(flag), _p(inv), _p(sc))
 
 
 def run_baseline(compiled: CompiledEnv, n_envs: int, steps: int, seed: int, with_obs: bool, n_threads: int) -> float:

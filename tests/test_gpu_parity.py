@@ -1,0 +1,349 @@
+"""Parity of the CUDA step path (through the C ABI) against the reference's golden traces and the CPU oracle.
+
+Bar: bit-exact grid / positions / HP / flags / inventory / dones / observations / masks / statistics;
+rewards and metadata exact in fp32 (compared as bit patterns).
+"""
+import numpy as np
+import pytest
+import torch
+
+import traces
+from helpers import STATE_KEYS, bits, compiled, golden_ids, golden_traces
+from marl_ctf_development_b200 import experiment_env_config
+from oracle.ctf_oracle import OracleBatch
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(exp, B, **kw):
+    from marl_ctf_development_b200 import GridworldCtfGPU
+
+    ec = experiment_env_config(exp)
+    ec.update(kw.pop("env_overrides", {}))
+    return GridworldCtfGPU(**ec, num_envs=B, device="cuda:0", **kw)
+
+
+def _assert_batch_state(env, orc, where, keys=STATE_KEYS + ("step", "episode")):
+    st, so = env.get_state(), orc.state()
+    for k in keys:
+        got, want = np.asarray(st[k]).astype(np.int64), np.asarray(so[k]).astype(np.int64)
+        if not np.array_equal(got, want):
+            bad = np.argwhere(got.reshape(got.shape[0], -1) != want.reshape(want.shape[0], -1))[0][0]
+            raise AssertionError(f"{where}: {k} differs in env {bad}\n got={got[bad]}\nwant={want[bad]}")
+
+
+def _assert_obs(env, orc, where, u8=False):
+    o_ref, m_ref = orc.observe(u8=u8)
+    assert np.array_equal(env.obs.cpu().numpy(), o_ref), where + ": observations differ"
+    assert np.array_equal(bits(env.meta.cpu().numpy()), bits(m_ref)), where + ": metadata differs"
+
+
+# ---------------------------------------------------------------------------------------------------
+# 1. the reference's own traces (tests/golden, generated from the unmodified reference)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("exp,kind,path", golden_traces(), ids=golden_ids())
+def test_cuda_replays_reference_trace(exp, kind, path):
+    tr = np.load(path)
+    B, slot = 37, 5  # the golden env sits at batch index 5; ragged last CTA on purpose
+    env = _env(exp, B, seed=int(tr["seed"]), env_id_base=int(tr["env_id"]) - slot, stats="full")
+    rng = np.random.default_rng(1)
+    t, oi = 0, 0
+    for episode, steps in enumerate(tr["episode_lengths"]):
+        if episode:
+            env.reset()
+        assert tr["obs_steps"][oi] == t
+        assert np.array_equal(env.obs[slot].cpu().numpy(), tr["obs"][oi].astype(np.float32)), f"reset obs ep{episode}"
+        assert np.array_equal(bits(env.meta[slot].cpu().numpy()), bits(tr["meta"][oi]))
+        oi += 1
+        for _ in range(int(steps)):
+            a = rng.integers(0, 9, (B, env.N_AGENTS)).astype(np.uint8)
+            a[slot] = tr["actions"][t]
+            obs, meta, rew, done, mask = env.step(torch.from_numpy(a).cuda())
+            st = env.get_state()
+            for k in STATE_KEYS:
+                assert np.array_equal(st[k][slot].astype(np.int64), tr[k][t].astype(np.int64)), f"{exp}/{kind} t={t} {k}"
+            assert np.array_equal(bits(rew[slot].cpu().numpy()), bits(tr["rewards"][t])), f"t={t} rewards"
+            assert bool(done[slot].item()) == bool(tr["done"][t])
+            assert int(st["episode"][slot]) == episode
+            t += 1
+            if traces.snap_after_step(t, int(st["step"][slot]), env.GAME_STEPS):
+                assert tr["obs_steps"][oi] == t
+                assert np.array_equal(obs[slot].cpu().numpy(), tr["obs"][oi].astype(np.float32)), f"t={t} obs"
+                assert np.array_equal(bits(meta[slot].cpu().numpy()), bits(tr["meta"][oi])), f"t={t} meta"
+                oi += 1
+        st = env.get_state()
+        assert np.array_equal(st["stats"][slot], tr["stats"][episode]), f"stats ep{episode}"
+        assert np.array_equal(st["visits"][slot], tr["visits"][episode]), f"visits ep{episode}"
+    assert oi == len(tr["obs_steps"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# 2. BASELINE.json configs against the oracle on seeded traces
+# ---------------------------------------------------------------------------------------------------
+def _run_against_oracle(exp, B, steps, policy, seed, obs_every, stats="counters", obs_dtype=torch.float32, **kw):
+    env = _env(exp, B, seed=seed, env_id_base=1000, stats=stats, obs_dtype=obs_dtype, **kw)
+    orc = OracleBatch(env.ce, B, seed=seed, env_id_base=1000)
+    u8 = obs_dtype == torch.uint8
+    _assert_obs(env, orc, "reset", u8)
+    rng = np.random.default_rng(seed)
+    pol = traces.make_policy(policy, env.ce) if policy != "uniform" else None
+    for t in range(steps):
+        if pol is None:
+            a = rng.integers(0, 9, (B, env.N_AGENTS)).astype(np.uint8)
+        else:
+            st = orc.state()
+            a = np.stack([pol(rng, st["pos"][b], st["has_flag"][b]) for b in range(B)])
+        _, _, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+        r_ref, d_ref = orc.step(a)
+        assert np.array_equal(bits(rew.cpu().numpy()), bits(r_ref)), f"{exp} t={t}: rewards differ"
+        assert np.array_equal(done.cpu().numpy(), d_ref), f"{exp} t={t}: dones differ"
+        if t % obs_every == 0 or t == steps - 1:
+            _assert_batch_state(env, orc, f"{exp} t={t}")
+            _assert_obs(env, orc, f"{exp} t={t}", u8)
+    st, so = env.get_state(), orc.state()
+    if stats != "none":
+        assert np.array_equal(st["stats"], so["stats"]), "statistics differ"
+        assert np.array_equal(env.stats_sum(all_reduce=False).cpu().numpy(), so["stats"].sum(0)), "stats_sum differs"
+    if stats == "full":
+        assert np.array_equal(st["visits"], so["visits"])
+    return env, orc
+
+
+def test_config2_the_split_4096_envs_full_episode():
+    """BASELINE configs[1]: 0_the_split, B=4096, bit-exact over a whole 500-step episode + 2 steps past done."""
+    _run_against_oracle("0_the_split", 4096, 502, "uniform", seed=11, obs_every=125)
+
+
+def test_config2_the_split_seek_policy_captures():
+    env, orc = _run_against_oracle("0_the_split", 256, 500, "seek", seed=12, obs_every=50)
+    assert orc.state()["captures"].sum() > 50  # the capture / adjusted / terminal reward paths fired
+
+
+def test_config3_gridlocked_builder_paths():
+    """BASELINE configs[2] semantics: miners (2->3->0, place) and vaulters (wall-jump, HP gate) on 7_gridlocked."""
+    env, orc = _run_against_oracle("7_gridlocked", 512, 500, "builder", seed=13, obs_every=50, stats="full")
+    s = orc.state()["stats"].sum(0).sum(1)
+    assert s[5] > 0 and s[6] > 0 and s[1] > 0 and s[3] > 0  # laid, mined, respawns, captures
+
+
+def test_config3_gridlocked_16384_envs_uniform():
+    _run_against_oracle("7_gridlocked", 16384, 120, "uniform", seed=14, obs_every=119)
+
+
+def test_config4_arena_seek_and_uniform():
+    _run_against_oracle("8_arena", 512, 500, "seek", seed=15, obs_every=50, stats="full")
+    _run_against_oracle("8_arena", 2048, 150, "uniform", seed=16, obs_every=75)
+
+
+def test_uint8_observations_all_alignments():
+    # 7_gridlocked: E = 13182 bytes per env -> every 16-byte phase occurs across envs
+    _run_against_oracle("7_gridlocked", 67, 60, "builder", seed=17, obs_every=10, obs_dtype=torch.uint8)
+    _run_against_oracle("8_arena", 33, 60, "seek", seed=18, obs_every=10, obs_dtype=torch.uint8)
+
+
+@pytest.mark.parametrize("exp", ["1_fence", "2_jailbreak", "3_one_way_out", "4_keyhole", "5_skittles", "6_the_wall"])
+def test_other_experiments_against_oracle(exp):
+    _run_against_oracle(exp, 128, 260, "builder", seed=19, obs_every=20, stats="full")
+
+
+def test_no_stats_variant_matches():
+    _run_against_oracle("8_arena", 130, 80, "seek", seed=20, obs_every=20, stats="none")
+
+
+# ---------------------------------------------------------------------------------------------------
+# 3. full BASELINE size: size-independent properties + a checked subset
+# ---------------------------------------------------------------------------------------------------
+def test_config4_full_size_properties_and_subset():
+    B, steps, seed = 65536, 40, 21
+    env = _env("8_arena", B, seed=seed, stats="counters")
+    N, G = env.N_AGENTS, env.GRID_SIZE
+    sub = np.sort(np.random.default_rng(0).choice(B, 256, replace=False))
+    # oracle envs for the subset only (global env id = batch index)
+    orcs = [OracleBatch(env.ce, 1, seed=seed, env_id_base=int(b)) for b in sub]
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(steps):
+        a = torch.randint(0, 9, (B, N), dtype=torch.uint8, device="cuda", generator=gen)
+        _, _, rew, done, _ = env.step(a)
+        a_sub = a[torch.from_numpy(sub).cuda()].cpu().numpy()
+        for i, o in enumerate(orcs):
+            r_ref, _ = o.step(a_sub[i : i + 1])
+            assert np.array_equal(bits(rew[int(sub[i])].cpu().numpy()), bits(r_ref[0]))
+    st = env.get_state()
+    for i, o in enumerate(orcs):
+        so = o.state()
+        for k in STATE_KEYS:
+            assert np.array_equal(st[k][sub[i]].astype(np.int64), so[k][0].astype(np.int64)), (k, int(sub[i]))
+    o_ref = np.concatenate([o.observe()[0] for o in orcs])
+    assert np.array_equal(env.obs[torch.from_numpy(sub).cuda()].cpu().numpy(), o_ref)
+    # properties over all 65536 envs
+    grid, pos = torch.from_numpy(st["grid"]).long(), torch.from_numpy(st["pos"]).long()
+    tiles = torch.tensor([env.AGENT_TILE_MAP[i] for i in range(N)])
+    at_pos = grid[torch.arange(B)[:, None], pos[..., 0], pos[..., 1]]
+    assert bool((at_pos == tiles[None]).all()), "every agent's tile sits at its recorded position"
+    for tile in range(4, 12):
+        assert bool(((grid == tile).sum((1, 2)) == (tiles == tile).sum()).all()), "agent tiles are conserved"
+    hp = torch.from_numpy(st["hp_q"])
+    mx = torch.tensor([env.ce.cfg.hp_max_q[env.AGENT_TYPES[i]] for i in range(N)])
+    assert bool(((hp > 0) & (hp <= mx[None])).all())
+    flag = torch.from_numpy(st["has_flag"]).long()
+    for team in (0, 1):
+        fr, fc = env.FLAG_POSITIONS[team]
+        home = grid[:, fr, fc] == 12 + team
+        carried = flag[:, [i for i in range(N) if env.AGENT_TEAMS[i] != team]].sum(1)
+        assert bool((home == (carried == 0)).all()) and bool((carried <= 1).all()), "a flag is home xor carried by one opponent"
+    obs = env.obs
+    assert bool((obs[:, :, 0].sum((2, 3)) == 1).all()), "self plane is one-hot"
+    nonopen = torch.from_numpy((st["grid"] != 0).sum((1, 2))).cuda().float()
+    assert bool((obs[:, :, 1:].sum((2, 3, 4)) == nonopen[:, None]).all()), "8_arena: every non-open cell is in exactly one channel"
+    assert bool(((obs == 0) | (obs == 1)).all())
+    assert int(st["step"].min()) == steps and int(st["step"].max()) == steps
+
+
+def test_results_do_not_depend_on_sharding_or_batch_order():
+    """Env b of a 1024-env batch equals env b - 512 of a shard created with env_id_base=512 (multi-GPU partition rule)."""
+    seed, steps = 22, 60
+    full = _env("8_arena", 1024, seed=seed)
+    shard = _env("8_arena", 512, seed=seed, env_id_base=512)
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    for _ in range(steps):
+        a = torch.randint(0, 9, (1024, full.N_AGENTS), dtype=torch.uint8, device="cuda", generator=gen)
+        full.step(a)
+        shard.step(a[512:].contiguous())
+    assert torch.equal(full.obs[512:], shard.obs) and torch.equal(full.meta[512:], shard.meta)
+    assert torch.equal(full.rewards[512:], shard.rewards)
+    sf, ss = full.get_state(), shard.get_state()
+    for k in STATE_KEYS:
+        assert np.array_equal(sf[k][512:], ss[k])
+
+
+def test_determinism_and_seed_sensitivity():
+    outs = []
+    for seed in (30, 30, 31):
+        env = _env("8_arena", 300, seed=seed)
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        for _ in range(50):
+            env.step(torch.randint(0, 9, (300, env.N_AGENTS), dtype=torch.uint8, device="cuda", generator=gen))
+        outs.append(env.get_state())
+    assert all(np.array_equal(outs[0][k], outs[1][k]) for k in STATE_KEYS)
+    assert any(not np.array_equal(outs[0][k], outs[2][k]) for k in STATE_KEYS)
+
+
+# ---------------------------------------------------------------------------------------------------
+# 4. edge cases of the boundary
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 3, 4, 5])
+def test_tiny_and_ragged_batches(B):
+    _run_against_oracle("8_arena", B, 30, "seek", seed=40 + B, obs_every=5, stats="full")
+
+
+def test_step_from_injected_states_round_trip():
+    """set_state -> step equals the oracle stepped from the same injected state (flag carried next to home, low HP)."""
+    B = 64
+    env = _env("8_arena", B, seed=50, stats="none")
+    orc = OracleBatch(env.ce, B, seed=50)
+    rng = np.random.default_rng(3)
+    for t in range(25):
+        a = rng.integers(0, 9, (B, env.N_AGENTS)).astype(np.uint8)
+        orc.step(a)
+    so = orc.state()
+    so["hp_q"] = np.maximum(1, so["hp_q"] - rng.integers(0, 30, so["hp_q"].shape)).astype(np.int32)  # many agents near death
+    so["step"][:] = 497  # three steps before the terminal step
+    args = (so["grid"], so["pos"], so["hp_q"], so["has_flag"], so["inventory"], so["step"], so["episode"], so["captures"])
+    orc.set_state(*args)
+    env.set_state(*args)
+    for t in range(6):
+        a = rng.integers(0, 9, (B, env.N_AGENTS)).astype(np.uint8)
+        _, _, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+        r_ref, d_ref = orc.step(a)
+        assert np.array_equal(bits(rew.cpu().numpy()), bits(r_ref))
+        assert np.array_equal(done.cpu().numpy(), d_ref)
+        _assert_batch_state(env, orc, f"injected t={t}")
+        _assert_obs(env, orc, f"injected t={t}")
+    assert done.all()
+
+
+def test_out_of_range_action_faults_like_keyerror():
+    env = _env("0_the_split", 8, seed=1, validate_actions=True)
+    a = torch.full((8, env.N_AGENTS), 4, dtype=torch.uint8, device="cuda")
+    env.step(a)
+    a[3, 1] = 9
+    with pytest.raises(KeyError):
+        env.step(a)
+
+
+def test_observe_with_explicit_reverse_flags_and_symmetry():
+    env = _env("8_arena", 16, seed=2)
+    orc = OracleBatch(env.ce, 16, seed=2)
+    rng = np.random.default_rng(4)
+    for _ in range(30):
+        a = rng.integers(0, 9, (16, env.N_AGENTS)).astype(np.uint8)
+        env.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+    for flags in ([0] * 8, [1] * 8, [1, 0, 0, 1, 1, 0, 1, 0]):
+        obs, meta = env.observe(reverse_flags=flags, into_new=True)
+        o_ref, m_ref = orc.observe(reverse_flags=flags)
+        assert np.array_equal(obs.cpu().numpy(), o_ref)
+        assert np.array_equal(bits(meta.cpu().numpy()), bits(m_ref))
+
+
+def test_reverse_team1_actions_folded_into_step():
+    B = 32
+    plain = _env("0_the_split", B, seed=3)
+    folded = _env("0_the_split", B, seed=3, reverse_team1_actions=True)
+    lut = plain.reversed_action_lut()
+    team1 = torch.tensor([plain.AGENT_TEAMS[i] == 1 for i in range(plain.N_AGENTS)], device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    for _ in range(40):
+        a = torch.randint(0, 9, (B, plain.N_AGENTS), device="cuda", generator=gen)
+        plain.step(torch.where(team1[None], lut[a], a).to(torch.uint8))  # what ppo.py:84-93 / utils.py:549 do on the host
+        folded.step(a.to(torch.uint8))
+    assert torch.equal(plain.obs, folded.obs) and torch.equal(plain.rewards, folded.rewards)
+
+
+def test_step_host_matches_device_step():
+    B = 48
+    dev = _env("8_arena", B, seed=4)
+    host = _env("8_arena", B, seed=4)
+    a_h = torch.empty((B, dev.N_AGENTS), dtype=torch.uint8).pin_memory()
+    r_h = torch.empty((B, dev.N_AGENTS), dtype=torch.float32).pin_memory()
+    d_h = torch.empty((B,), dtype=torch.uint8).pin_memory()
+    rng = np.random.default_rng(9)
+    for _ in range(20):
+        a_h.copy_(torch.from_numpy(rng.integers(0, 9, (B, dev.N_AGENTS)).astype(np.uint8)))
+        dev.step(a_h.cuda())
+        host.step_host(a_h, r_h, d_h)
+        assert torch.equal(dev.rewards.cpu(), r_h) and torch.equal(dev.dones.cpu(), d_h)
+    assert torch.equal(dev.obs, host.obs)
+
+
+def test_outputs_written_into_caller_buffers():
+    B = 20
+    env = _env("0_the_split", B, seed=5)
+    N, C, G, M = env.N_AGENTS, env.n_channels, env.GRID_SIZE, env.meta_size
+    big = torch.zeros((3, B, N, C, G, G), device="cuda")
+    env.bind_outputs(obs=big[1])
+    env.step(torch.full((B, N), 4, dtype=torch.uint8, device="cuda"))
+    assert float(big[1].sum()) > 0 and float(big[0].sum()) == 0 and float(big[2].sum()) == 0
+
+
+def test_action_mask_and_dims():
+    env = _env("8_arena", 4, seed=6)
+    assert tuple(env.action_mask.shape) == (4, 8, 9)
+    want = [[1] * 5 + [0] * 4 if env.AGENT_TYPES[i] in (0, 1) else [1] * 9 for i in range(8)]
+    assert env.action_mask[2].cpu().tolist() == want
+    assert env.get_env_dims() == ((14, 15, 15), (13, 15, 15), (22,), (115,))
+
+
+def test_half_rounding_on_device_matches_numpy():
+    """metadata[0:2] go through float16 (gridworld_ctf.py:1044): check every step fraction and many capture ratios."""
+    env = _env("8_arena", 1, seed=7)
+    st = env.get_state()
+    for step, c0, c1 in [(s, (s * 7) % 61, (s * 13) % 59) for s in range(0, 1001, 3)]:
+        st["step"][:] = step
+        st["captures"][:] = (c0, c1)
+        env.set_state(st["grid"], st["pos"], st["hp_q"], st["has_flag"], st["inventory"], st["step"], st["episode"], st["captures"])
+        _, meta = env.observe(into_new=True)
+        m = meta[0].cpu().numpy()
+        assert m[0, 0] == np.float32(np.float16(step / 500))
+        assert m[0, 1] == np.float32(np.float16((c0 + 1) / (c1 + 1)))
+        assert m[1, 1] == np.float32(np.float16((c1 + 1) / (c0 + 1)))
