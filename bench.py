@@ -180,7 +180,8 @@ def run_ours(args) -> dict | None:
     B, K, W = args.envs, args.steps, args.warmup
     ec = experiment_env_config(EXPERIMENT)
     env = GridworldCtfGPU(**ec, num_envs=B, device=dev, seed=args.seed, env_id_base=rank * B,
-                          stats="none" if args.no_stats else "counters")
+                          stats="none" if args.no_stats else "counters",
+                          obs_dtype=torch.float32 if args.obs_dtype == "float32" else torch.uint8)
     N, G, C = env.N_AGENTS, env.GRID_SIZE, env.n_channels
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 8  # distinct pre-generated action tensors, resident in HBM before the timed region
@@ -251,7 +252,7 @@ def run_ours(args) -> dict | None:
     if rank == 0:
         agent_steps = world * B * N * K
         value = agent_steps / (ms * 1e-3)
-        per_agent_step = algorithmic_bytes_per_agent_step(G, N, C)
+        per_agent_step = algorithmic_bytes_per_agent_step(G, N, C, 4 if args.obs_dtype == "float32" else 1)
         launch_s = ms * 1e-3 / K
         achieved = per_agent_step * B * N / launch_s / 1e9
         peak, peak_src = measured_hbm_peak()
@@ -260,7 +261,7 @@ def run_ours(args) -> dict | None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": workload_config(B, world),
+            "config": dict(workload_config(B, world), obs_dtype=args.obs_dtype),
             "clocks": clocks,
             "e2e": {
                 "value": world * B * N * Ke / (e2e_ms * 1e-3), "unit": UNIT,
@@ -271,7 +272,7 @@ def run_ours(args) -> dict | None:
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["bytes_per_launch"] if traffic and traffic.get("envs_per_gpu") == B else None,
-                "kernel": "k_step<float,%s>" % ("false" if args.no_stats else "true"),
+                "kernel": "k_step<%s,%s>" % ("float" if args.obs_dtype == "float32" else "uint8_t", "false" if args.no_stats else "true"),
                 "algorithmic_bytes_per_agent_step": per_agent_step,
                 "bytes_per_launch": per_agent_step * B * N,
                 "launch_ms": launch_s * 1e3,
@@ -280,11 +281,13 @@ def run_ours(args) -> dict | None:
             "episode_stats_checksum": int(stats_total.sum().item()),
         }
         if world == 1 and not args.no_cpu_baseline:
-            t0 = time.perf_counter()
-            batch, ce, threads, n_envs = cpu_leg(envs_per_thread=16, steps=0)
-            steps = 100
+            # bounded sample (~12 s) of the same workload on the host cores, reported beside the GPU number
+            batch, ce, threads, n_envs = cpu_leg(envs_per_thread=64, steps=0)
+            steps, chunk = 0, 25
             t1 = time.perf_counter()
-            batch.run(steps, 7, True, threads)
+            while time.perf_counter() - t1 < 12.0:
+                batch.run(chunk, 7 + steps, True, threads)
+                steps += chunk
             dt = time.perf_counter() - t1
             result["cpu_baseline"] = {
                 "value": n_envs * N * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
@@ -307,6 +310,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-stats", action="store_true", help="skip the episode-statistics counters")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--obs-dtype", choices=["float32", "uint8"], default="float32",
+                    help="float32 is the drop-in default and the headline; uint8 is reported separately")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 
