@@ -303,7 +303,7 @@ def run_ours(args) -> dict | None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU (BASELINE.json: 65536)")
     ap.add_argument("--seed", type=int, default=0)
