@@ -7,7 +7,8 @@ import os
 from .config import CtfConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libctf_b200.so")
+# CTF_B200_LIB selects another build of the same extension (kernel A/B experiments); default is the in-tree one
+LIB_PATH = os.environ.get("CTF_B200_LIB") or os.path.join(_HERE, "libctf_b200.so")
 
 # every symbol include/ctf_b200.h declares
 EXPORTS = (

@@ -45,14 +45,14 @@ struct DevPlan {
     int heal_q, vault_cost_q, vault_min_q;
     int zone_distance, guardian_distance, tagging_range, max_agent_blocks, block_pickup_value;
     int hp_max_q[4], damage_q[4], damage_boosted_q[4];
-    int warp_smem_bytes, stats_off, list_off, bits_off;
+    int warp_smem_bytes, list_off, bits_off;
     unsigned char team[8], type[8], tile[8], start_r[8], start_c[8], obs_rev[8], meta_hp_src[8];
     signed char my_slot[8];        // index of agent i in OPPONENTS[1 - team(i)], -1 if truncated away
     unsigned char n_opp[2];
     unsigned char flag_pos[2][2], capture_pos[2][2], spawn_pos[2][2], flag_tile[2];
     signed char delta[4][9][2];
     unsigned char rev_action[16];
-    unsigned char meta_agent[8][8];  // metadata slot q of observer a -> agent id (0xFF = none)
+    unsigned int meta_row[8];        // metadata slots of observer a: nibble q -> agent id (0xF = none)
     unsigned char grid_template[kGridBytes];  // 16-stride rows
 };
 
@@ -107,7 +107,6 @@ __device__ __forceinline__ int ag_hp(uint32_t m) { return (int)(short)(m >> 16);
 
 struct WarpMem {
     uint8_t* grid;     // [256]
-    uint32_t* stats;   // [13*N] (valid when STATS)
     uint32_t* list;    // [256]
     uint32_t* bits;    // [bits_words]
 };
@@ -116,7 +115,6 @@ __device__ __forceinline__ WarpMem warp_mem(const DevPlan& P, unsigned char* sme
     unsigned char* base = smem + (size_t)warp * P.warp_smem_bytes;
     WarpMem w;
     w.grid = base;
-    w.stats = reinterpret_cast<uint32_t*>(base + P.stats_off);
     w.list = reinterpret_cast<uint32_t*>(base + P.list_off);
     w.bits = reinterpret_cast<uint32_t*>(base + P.bits_off);
     return w;
@@ -144,10 +142,11 @@ __device__ __forceinline__ uint4 expand_bits(uint32_t b);
 template <>
 __device__ __forceinline__ uint4 expand_bits<float>(uint32_t b) {  // 4 elements
     uint4 v;
-    v.x = (b & 1u) ? 0x3F800000u : 0u;
-    v.y = (b & 2u) ? 0x3F800000u : 0u;
-    v.z = (b & 4u) ? 0x3F800000u : 0u;
-    v.w = (b & 8u) ? 0x3F800000u : 0u;
+    // 1.0f = 0x3F800000 has 23 trailing zero bits, so (b & 2^k) * (0x3F800000 >> k) is exact for k <= 3
+    v.x = (b & 1u) * 0x3F800000u;
+    v.y = (b & 2u) * 0x1FC00000u;
+    v.z = (b & 4u) * 0x0FE00000u;
+    v.w = (b & 8u) * 0x07F00000u;
     return v;
 }
 
@@ -173,7 +172,7 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const WarpMem& w, ui
         const int n4 = (P.bits_words + 3) >> 2;
         for (int i = lane; i < n4; i += 32) b4[i] = make_uint4(0, 0, 0, 0);
     }
-    // 2. list the non-open cells: tile | dest(normal)<<8 | dest(flipped)<<16
+    // 2. list the non-open cells: channel(team-0 view) | channel(team-1 view)<<4 | dest(normal)<<8 | dest(flipped)<<16
     int count = 0;
 #pragma unroll
     for (int j = 0; j < kGridBytes / 32; ++j) {
@@ -183,29 +182,30 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const WarpMem& w, ui
         if (t != 0) {
             const int r = cell >> 4, c = cell & 15;
             const int pos = count + __popc(nz & ((1u << lane) - 1u));
-            w.list[pos] = t | ((uint32_t)(r * P.G + c) << 8) | ((uint32_t)flip_cell(P, r, c) << 16);
+            const uint32_t ch0 = (uint32_t)(P.lut64[0] >> (t * 4)) & 15u, ch1 = (uint32_t)(P.lut64[1] >> (t * 4)) & 15u;
+            w.list[pos] = ch0 | (ch1 << 4) | ((uint32_t)(r * P.G + c) << 8) | ((uint32_t)flip_cell(P, r, c) << 16);
         }
         count += __popc(nz);
     }
     __syncwarp();
-    // 3. scatter: every agent's view of every non-open cell + its own position plane (channel 0)
-    for (int a = 0; a < N; ++a) {
-        const int team = P.team[a];
+    // 3. scatter: lane l works for agent (l & 7) on list entries (l >> 3), (l >> 3) + 4, ...; lane a < N also sets
+    //    agent a's own position plane (channel 0) from its registers
+    {
+        const int a = lane & 7;
+        const bool valid = a < N;
         const bool rev = (rev_mask >> a) & 1u;
-        const unsigned long long lut = P.lut64[team];
+        const int ch_shift = P.team[a] ? 4 : 0, p_shift = rev ? 16 : 8;
         const int base = a * CGG;
-        for (int k = lane; k < count; k += 32) {
+        for (int k = lane >> 3; k < count; k += 4) {
             const uint32_t ent = w.list[k];
-            const int ch = (int)((lut >> ((ent & 15u) * 4)) & 15ull);
-            if (ch) {
-                const int p = rev ? (ent >> 16) & 0xFF : (ent >> 8) & 0xFF;
-                const int e = base + ch * GG + p;
+            const int ch = (ent >> ch_shift) & 15;
+            if (valid && ch) {
+                const int e = base + ch * GG + (int)((ent >> p_shift) & 0xFFu);
                 atomicOr(&w.bits[e >> 5], 1u << (e & 31));
             }
         }
-        const uint32_t ma = __shfl_sync(kFull, me, a);
-        if (lane == 0) {
-            const int r = ag_r(ma), c = ag_c(ma);
+        if (lane < N) {
+            const int r = ag_r(me), c = ag_c(me);
             const int e = base + (rev ? flip_cell(P, r, c) : r * P.G + c);
             atomicOr(&w.bits[e >> 5], 1u << (e & 31));
         }
@@ -245,27 +245,25 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const WarpMem& w, ui
 __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int step, int caps0, int caps1,
                                            float* __restrict__ meta_env, int lane) {
     const int N = P.N, M = P.M;
-    // hp8[i] = uint8(agent_hp[TYPE_i as agent id] / AGENT_TYPE_HP[TYPE_i])  (:1039-1041)
     const int li = lane & 7;
+    // hp8[i] = uint8(agent_hp[TYPE_i as agent id] / AGENT_TYPE_HP[TYPE_i])  (:1039-1041); lane i keeps hp8 | has_flag<<8
     const uint32_t src = __shfl_sync(kFull, me, P.meta_hp_src[li]);
-    const int hp8 = (ag_hp(src) / P.hp_max_q[P.type[li]]) & 0xFF;
-    const float pct = __half2float(__double2half((double)step / (double)P.game_steps));
-    const float ratio0 = __half2float(__double2half((double)(caps0 + 1) / (double)(caps1 + 1)));
-    const float ratio1 = __half2float(__double2half((double)(caps1 + 1) / (double)(caps0 + 1)));
+    const uint32_t pair = (uint32_t)((ag_hp(src) / P.hp_max_q[P.type[li]]) & 0xFF) | ((uint32_t)ag_flag(me) << 8);
+    // the three fp64 quotients that go through float16 (:1035-1036, :1044), one per lane, in a single pass
+    const int num = lane == 0 ? step : (lane == 1 ? caps0 + 1 : caps1 + 1);
+    const int den = lane == 0 ? P.game_steps : (lane == 1 ? caps1 + 1 : caps0 + 1);
+    const float quot = __half2float(__double2half((double)num / (double)den));
+    const float pct = __shfl_sync(kFull, quot, 0);
+    const float ratio0 = __shfl_sync(kFull, quot, 1), ratio1 = __shfl_sync(kFull, quot, 2);
+    const int m = lane;                       // lane m produces element m of each agent's vector
+    const int q4 = m >= 6 ? ((m - 6) >> 1) * 4 : 0;
     for (int a = 0; a < N; ++a) {
-        // lane m produces element m of agent a's vector
-        const int m = lane;
-        int q = (m - 6) >> 1;
-        q = q < 0 ? 0 : (q > 7 ? 7 : q);
-        const int srcAgent = P.meta_agent[a][q];
-        const int sl = srcAgent < 8 ? srcAgent : 0;
-        const int s_hp8 = __shfl_sync(kFull, hp8, sl);
-        const uint32_t s_me = __shfl_sync(kFull, me, sl);
-        float v = 0.0f;
-        if (m == 0) v = pct;
-        else if (m == 1) v = P.team[a] == 0 ? ratio0 : ratio1;
-        else if (m < 6) v = (m - 2 == P.type[a]) ? 1.0f : 0.0f;
-        else if (srcAgent < 8) v = ((m - 6) & 1) ? (float)ag_flag(s_me) : (float)s_hp8;
+        const uint32_t srcAgent = (P.meta_row[a] >> q4) & 15u;
+        const uint32_t sp = __shfl_sync(kFull, pair, srcAgent & 7u);
+        float v;
+        if (m >= 6) v = srcAgent == 15u ? 0.0f : (float)((m & 1) ? (sp >> 8) : (sp & 0xFFu));
+        else if (m >= 2) v = (m - 2 == P.type[a]) ? 1.0f : 0.0f;
+        else v = m == 0 ? pct : (P.team[a] == 0 ? ratio0 : ratio1);
         if (m < M) meta_env[a * M + m] = v;
     }
 }
@@ -287,10 +285,19 @@ __device__ __forceinline__ void store_state(const DevPlan& P, const Launch& L, c
     if (lane == 0) L.envs[env] = ev;
 }
 
+// Per-step counter deltas of this lane's agent, 4 bits per metric (every per-step increment is <= 15:
+// at most 4 tags / respawns / neighbours, distances <= GRID_SIZE - 1); added to the HBM counters once per step.
+struct Deltas {
+    uint32_t lo = 0, hi = 0;  // metrics 0..7, 8..12
+};
+
 template <bool STATS>
-__device__ __forceinline__ void bump(const WarpMem& w, const DevPlan& P, int metric, int agent, uint32_t by, int lane) {
+__device__ __forceinline__ void bump(Deltas& d, int metric, int agent, uint32_t by, int lane) {
     if (STATS) {
-        if (lane == 0) w.stats[metric * P.N + agent] += by;
+        if (lane == agent) {
+            if (metric < 8) d.lo += by << (4 * metric);
+            else d.hi += by << (4 * (metric - 8));
+        }
     }
 }
 
@@ -383,10 +390,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
         action = L.actions[env * N + lane];
     }
     uint4 ev = L.envs[env];
-    if (STATS) {
-        const int ns = CTF_N_METRICS * N;
-        for (int i = lane; i < ns; i += 32) w.stats[i] = L.stats[env * ns + i];
-    }
+    Deltas dl;
     const int my_team = P.team[li], my_type = P.type[li], my_slot = P.my_slot[li];
     const bool bad_action = lane < N && action >= CTF_N_ACTIONS;
     if (__any_sync(kFull, bad_action)) {
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
                     __syncwarp();
                     w.grid[ofr * kRow + ofc] = 1;
                     __syncwarp();
-                    bump<STATS>(w, P, CTF_M_FLAG_PICKUPS, a, 1, lane);
+                    bump<STATS>(dl, CTF_M_FLAG_PICKUPS, a, 1, lane);
                 }
                 if (cheb(nr, nc, hfr, hfc) <= 1 && aflag == 1 &&
                     (!P.home_flag_capture || w.grid[hfr * kRow + hfc] == P.flag_tile[team])) {        // capture (:594-610)
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
                     if (team == 0) caps0 += 1; else caps1 += 1;
                     cap_team |= 1u << team;
                     cap_now = true;
-                    bump<STATS>(w, P, CTF_M_FLAG_CAPTURES, a, 1, lane);
+                    bump<STATS>(dl, CTF_M_FLAG_CAPTURES, a, 1, lane);
                 }
                 if (act_code >= 5 && type == 2) ahp -= P.vault_cost_q;                               // (:652-657)
             } else if (act_code >= 5 && type == 3 && ainv > 0 && target == 0 &&
@@ -466,10 +470,10 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
                 __syncwarp();
                 ainv -= 1;
                 if (STATS) {
-                    bump<STATS>(w, P, CTF_M_BLOCKS_LAID, a, 1, lane);
-                    bump<STATS>(w, P, CTF_M_BLOCKS_LAID_DIST_OWN_FLAG, a,
+                    bump<STATS>(dl, CTF_M_BLOCKS_LAID, a, 1, lane);
+                    bump<STATS>(dl, CTF_M_BLOCKS_LAID_DIST_OWN_FLAG, a,
                                 (uint32_t)cheb(ar, ac, P.capture_pos[team][0], P.capture_pos[team][1]), lane);
-                    bump<STATS>(w, P, CTF_M_BLOCKS_LAID_DIST_OPP_FLAG, a,
+                    bump<STATS>(dl, CTF_M_BLOCKS_LAID_DIST_OPP_FLAG, a,
                                 (uint32_t)cheb(ar, ac, P.capture_pos[1 - team][0], P.capture_pos[1 - team][1]), lane);
                 }
             } else if (act_code < 5 && type == 3 && (target == 2 || target == 3)) {
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
                 __syncwarp();
                 if (target == 3) {
                     if (ainv < P.max_agent_blocks) ainv += P.block_pickup_value;
-                    bump<STATS>(w, P, CTF_M_BLOCKS_MINED, a, 1, lane);
+                    bump<STATS>(dl, CTF_M_BLOCKS_MINED, a, 1, lane);
                 }
             }
         }
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
             if (hit) me = (me & 0xFFFFu) | ((uint32_t)(hp & 0xFFFF) << 16);
             const unsigned hits = __ballot_sync(kFull, hit);
             unsigned deaths = __ballot_sync(kFull, lethal);
-            if (STATS && hits) bump<STATS>(w, P, CTF_M_TAG_COUNT, a, (uint32_t)__popc(hits), lane);
+            if (STATS && hits) bump<STATS>(dl, CTF_M_TAG_COUNT, a, (uint32_t)__popc(hits), lane);
             // lethal hits respawn one after the other in opponent-id order: each changes the next one's window
             while (deaths) {
                 const int opp = __ffs(deaths) - 1;
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
                 const uint32_t om = __shfl_sync(kFull, me, opp);
                 const uint32_t ow = __shfl_sync(kFull, pick_word, opp);
                 const int oteam = 1 - team;
-                if (ag_flag(om)) bump<STATS>(w, P, CTF_M_FLAG_DISPOSSESSIONS, a, 1, lane);
+                if (ag_flag(om)) bump<STATS>(dl, CTF_M_FLAG_DISPOSSESSIONS, a, 1, lane);
                 // respawn (:761-794): open cells of the clipped 3x3 window around the victim's spawn, row-major
                 const int x = P.spawn_pos[oteam][0], y = P.spawn_pos[oteam][1];
                 const int wr = x - 1 + lane / 3, wc = y - 1 + lane % 3;
@@ -536,7 +540,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
                     if (lane == opp) me = pack_agent(rr, rc, 0, P.hp_max_q[P.type[opp]]);
                 }
                 if (lane == a) tag_reward = true;
-                bump<STATS>(w, P, CTF_M_RESPAWN_TAG_COUNT, a, 1, lane);
+                bump<STATS>(dl, CTF_M_RESPAWN_TAG_COUNT, a, 1, lane);
             }
         }
 
@@ -544,13 +548,13 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
         if (STATS) {
             const int d_own = cheb(ar, ac, P.capture_pos[team][0], P.capture_pos[team][1]);
             const int d_opp = cheb(ar, ac, P.capture_pos[1 - team][0], P.capture_pos[1 - team][1]);
-            if (d_own <= P.zone_distance) bump<STATS>(w, P, CTF_M_STEPS_DEFENDING_ZONE, a, 1, lane);
-            if (d_opp <= P.zone_distance) bump<STATS>(w, P, CTF_M_STEPS_ATTACKING_ZONE, a, 1, lane);
+            if (d_own <= P.zone_distance) bump<STATS>(dl, CTF_M_STEPS_DEFENDING_ZONE, a, 1, lane);
+            if (d_opp <= P.zone_distance) bump<STATS>(dl, CTF_M_STEPS_ATTACKING_ZONE, a, 1, lane);
             const bool near = lane < N && my_slot >= 0 && cheb(ar, ac, ag_r(me), ag_c(me)) <= 1;
             const unsigned mates = __ballot_sync(kFull, near && my_team == team);   // includes the agent itself
             const unsigned opps = __ballot_sync(kFull, near && my_team != team);
-            if (mates) bump<STATS>(w, P, CTF_M_STEPS_ADJ_TEAMMATE, a, (uint32_t)__popc(mates), lane);
-            if (opps) bump<STATS>(w, P, CTF_M_STEPS_ADJ_OPPONENT, a, (uint32_t)__popc(opps), lane);
+            if (mates) bump<STATS>(dl, CTF_M_STEPS_ADJ_TEAMMATE, a, (uint32_t)__popc(mates), lane);
+            if (opps) bump<STATS>(dl, CTF_M_STEPS_ADJ_OPPONENT, a, (uint32_t)__popc(opps), lane);
         }
     }
 
@@ -585,8 +589,14 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
     __syncwarp();
     store_state(P, L, w, env, me, inv, ev, lane);
     if (STATS) {
-        const int ns = CTF_N_METRICS * N;
-        for (int i = lane; i < ns; i += 32) L.stats[env * ns + i] = w.stats[i];
+        if (lane < N) {   // fire-and-forget reductions: no load latency, nothing held in registers
+            uint32_t* sp = L.stats + env * (long long)(CTF_N_METRICS * N) + lane;
+#pragma unroll
+            for (int m = 0; m < CTF_N_METRICS; ++m) {
+                const uint32_t v = ((m < 8 ? dl.lo : dl.hi) >> (4 * (m & 7))) & 15u;
+                if (v) atomicAdd(sp + m * N, v);
+            }
+        }
         if (L.visits && lane < N) {   // update_visitation_map (:911), uint8 wrap
             uint8_t* v = L.visits + (env * N + lane) * (long long)P.GG + ag_r(me) * P.G + ag_c(me);
             *v = (uint8_t)(*v + 1);
@@ -717,13 +727,15 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
     // metadata slot order (:1050-1067): self, team-mates in id order without self, opponents in id order
     for (int a = 0; a < N; ++a) {
         int q = 0;
-        for (int s = 0; s < 8; ++s) P.meta_agent[a][s] = 0xFF;
-        P.meta_agent[a][q++] = (unsigned char)a;
+        unsigned int row = 0xFFFFFFFFu;
+        auto put = [&](int agent) { row = (row & ~(0xFu << (4 * q))) | ((unsigned)agent << (4 * q)); ++q; };
+        put(a);
         const int team = c.agent_team[a];
         for (int j = 0; j < c.n_opponents[1 - team]; ++j)
-            if (c.opponents[1 - team][j] != a && q < N) P.meta_agent[a][q++] = c.opponents[1 - team][j];
+            if (c.opponents[1 - team][j] != a && q < N) put(c.opponents[1 - team][j]);
         for (int j = 0; j < c.n_opponents[team]; ++j)
-            if (q < N) P.meta_agent[a][q++] = c.opponents[team][j];
+            if (q < N) put(c.opponents[team][j]);
+        P.meta_row[a] = row;
     }
     for (int r = 0; r < G; ++r)
         for (int cc = 0; cc < G; ++cc) {
@@ -733,8 +745,7 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
         }
     // shared-memory carve-up per warp
     int off = kGridBytes;
-    P.stats_off = off;
-    if (stats_level > 0) off += ((CTF_N_METRICS * N * 4 + 15) / 16) * 16;
+    (void)stats_level;
     P.list_off = off;
     off += kMaxList * 4;
     P.bits_off = off;

@@ -22,6 +22,7 @@ import torch
 
 from . import _native
 from .config import METRIC_NAMES, N_METRICS, compile_config, env_dims
+from .sharding import all_reduce_stats
 
 _STATS_LEVELS = {"none": 0, "counters": 1, "full": 2}
 _OBS_DTYPES = {torch.float32: 0, torch.uint8: 1}
@@ -320,8 +321,8 @@ class GridworldCtfGPU:
             raise RuntimeError("create the env with stats='counters' or 'full' to collect episode statistics")
         out = torch.empty((N_METRICS, self.N_AGENTS), dtype=torch.int64, device=self.device)
         _native.check(self._lib.ctf_stats_sum(self._handle, self._state_struct, C.c_void_p(out.data_ptr()), self._stream()))
-        if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM)
+        if all_reduce:
+            all_reduce_stats(out)
         return out
 
     def metrics_from_counters(self, counters: np.ndarray, visits=None) -> dict:

@@ -1,0 +1,145 @@
+"""Batched versions of the reference's two callers of the step path.
+
+``collect_rollout``  mirrors ``PPOTrainer.get_single_rollout`` (ppo.py:31-131) for B envs at once;
+``batched_duel``     mirrors ``utils.duel`` (utils.py:500-573).
+
+Instead of a Python loop over agents that builds one observation at a time, the step kernel has already
+written every agent's observation and metadata into ``env.obs`` / ``env.meta``; one policy forward per team
+handles ``B * agents_per_team`` samples.  Team-1 policies act in the flipped frame and their actions are mapped
+back by the kernel (``reverse_team1_actions=True``), as ppo.py:84-93 and utils.py:549 do with
+``get_reversed_action`` on the host.
+
+Policies are any module with the reference ``Agent`` methods on batched inputs
+(``get_action_and_value(grid, meta, use_action_mask)``, ``get_action(...)``), e.g. ``policy.CtfPolicy``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass
+class Rollout:
+    """Layout of ppo.py:298-305 with the env axis batched: index [step * apt + agent_offset, env]."""
+
+    grid_states: torch.Tensor      # [T*apt, B, C, G, G]
+    metadata_states: torch.Tensor  # [T*apt, B, M]
+    actions: torch.Tensor          # [T*apt, B]
+    use_action_mask: torch.Tensor  # [T*apt, B]
+    logprobs: torch.Tensor         # [T*apt, B]
+    rewards: torch.Tensor          # [T*apt, B]
+    dones: torch.Tensor            # [T*apt, B]  (never written by the reference, ppo.py:53 — kept zero)
+    values: torch.Tensor           # [T*apt, B]
+    next_grid_state: torch.Tensor  # [B, C, G, G]
+    next_metadata_state: torch.Tensor  # [B, M]
+    next_done: torch.Tensor        # [B]
+
+
+def _require_folded_reversal(env):
+    if not env.ce.cfg.reverse_team1_actions:
+        raise ValueError("create the env with reverse_team1_actions=True: team-1 policies act in the flipped frame")
+
+
+def _team_indices(env, team):
+    return [i for i in range(env.N_AGENTS) if env.AGENT_TEAMS[i] == team]
+
+
+@torch.no_grad()
+def collect_rollout(env, agent, opponent, train_team1=True, num_env_steps=None, obs_storage_dtype=torch.float32) -> Rollout:
+    """One rollout of every env (ppo.py:31-131).  ``train_team1=True`` trains team 0 (ppo.py:274-279).
+
+    num_env_steps defaults to GAME_STEPS (one episode per rollout, as num_steps == GAME_STEPS in every
+    experiment).  obs_storage_dtype=torch.uint8 stores the {0,1} observations packed 4x smaller.
+    """
+    _require_folded_reversal(env)
+    team = 0 if train_team1 else 1
+    mine, theirs = _team_indices(env, team), _team_indices(env, 1 - team)
+    apt = len(mine)
+    T = env.GAME_STEPS if num_env_steps is None else int(num_env_steps)
+    B, N, dev = env.num_envs, env.N_AGENTS, env.device
+    C, G, M = env.n_channels, env.GRID_SIZE, env.meta_size
+    mine_t = torch.tensor(mine, device=dev)
+    theirs_t = torch.tensor(theirs, device=dev)
+    mask_flags = env.use_action_mask  # [N] float, AGENT_TYPE_ACTION_MASK per agent
+
+    out = Rollout(
+        grid_states=torch.zeros((T * apt, B, C, G, G), dtype=obs_storage_dtype, device=dev),
+        metadata_states=torch.zeros((T * apt, B, M), device=dev),
+        actions=torch.zeros((T * apt, B), device=dev),
+        use_action_mask=torch.zeros((T * apt, B), device=dev),
+        logprobs=torch.zeros((T * apt, B), device=dev),
+        rewards=torch.zeros((T * apt, B), device=dev),
+        dones=torch.zeros((T * apt, B), device=dev),
+        values=torch.zeros((T * apt, B), device=dev),
+        next_grid_state=torch.empty(0), next_metadata_state=torch.empty(0), next_done=torch.empty(0),
+    )
+    obs, meta, _ = env.reset()                                                    # ppo.py:57
+    actions = torch.empty((B, N), dtype=torch.uint8, device=dev)
+    for t in range(T):
+        sl = slice(t * apt, (t + 1) * apt)
+        # trained team: [B, apt, ...] -> [apt, B, ...] so that buffer row = step*apt + agent_offset (ppo.py:74-79)
+        g = obs[:, mine_t].transpose(0, 1).contiguous()
+        m = meta[:, mine_t].transpose(0, 1).contiguous()
+        flags = mask_flags[mine_t].unsqueeze(1).expand(apt, B)
+        a, logp, _, v = agent.get_action_and_value(
+            g.reshape(apt * B, C, G, G).float(), m.reshape(apt * B, M), flags.reshape(apt * B)
+        )
+        out.grid_states[sl] = g.to(obs_storage_dtype)
+        out.metadata_states[sl] = m
+        out.values[sl] = v.reshape(apt, B)
+        out.actions[sl] = a.reshape(apt, B).float()
+        out.use_action_mask[sl] = flags
+        out.logprobs[sl] = logp.reshape(apt, B)
+        actions[:, mine_t] = a.reshape(apt, B).t().to(torch.uint8)
+        if theirs:
+            k = len(theirs)
+            go = obs[:, theirs_t].reshape(B * k, C, G, G).float()
+            mo = meta[:, theirs_t].reshape(B * k, M)
+            fo = mask_flags[theirs_t].unsqueeze(0).expand(B, k).reshape(B * k)
+            ao = opponent.get_action_and_value(go, mo, fo)[0]
+            actions[:, theirs_t] = ao.reshape(B, k).to(torch.uint8)
+        obs, meta, rewards, dones, _ = env.step(actions)                          # ppo.py:98
+        out.rewards[sl] = rewards[:, mine_t].t()                                  # ppo.py:106-109
+    first = min(mine)
+    out.next_grid_state = obs[:, first].clone().float()                           # ppo.py:116-118
+    out.next_metadata_state = meta[:, first].clone()
+    out.next_done = dones.float().clone()                                         # ppo.py:111
+    return out
+
+
+@torch.no_grad()
+def batched_duel(env, agent, opponent, max_steps=256, return_result=True):
+    """utils.duel (utils.py:500-573) for every env of the batch.
+
+    Team 0 acts with ``agent``, team 1 with ``opponent``.  Stops when the envs are done or after
+    max_steps + 1 steps (the reference's ``step_count > max_steps`` check runs after the step, :559-560).
+    Returns int tensor [B] of +1 / 0 / -1 (team-0 win / draw / loss by flag captures, :562-569), or the
+    all-reduced ``env.metrics`` dict when return_result=False (:571).
+    """
+    _require_folded_reversal(env)
+    B, N, dev = env.num_envs, env.N_AGENTS, env.device
+    C, G, M = env.n_channels, env.GRID_SIZE, env.meta_size
+    teams = [torch.tensor(_team_indices(env, t), device=dev) for t in (0, 1)]
+    policies = (agent, opponent)
+    obs, meta, _ = env.reset()
+    actions = torch.empty((B, N), dtype=torch.uint8, device=dev)
+    step_count = 0
+    while True:
+        step_count += 1
+        for idx, pol in zip(teams, policies):
+            k = idx.numel()
+            if k == 0:
+                continue
+            a = pol.get_action(
+                obs[:, idx].reshape(B * k, C, G, G).float(), meta[:, idx].reshape(B * k, M),
+                env.use_action_mask[idx].unsqueeze(0).expand(B, k).reshape(B * k),
+            )
+            actions[:, idx] = a.reshape(B, k).to(torch.uint8)
+        obs, meta, _, dones, _ = env.step(actions)
+        if step_count > max_steps or step_count >= env.GAME_STEPS:  # all envs finish in lock-step
+            break
+    if return_result:
+        caps = env._envs[:, 2:4].long()
+        return torch.sign(caps[:, 0] - caps[:, 1])
+    return env.episode_stats()

@@ -1,0 +1,200 @@
+"""Drop-in adapters on the GPU: the single-env view with the reference's surface, and the batched
+rollout / duel loops, each checked against the reference's caller loops run on the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import traces
+from helpers import bits, compiled, golden_traces
+from marl_ctf_development_b200 import experiment_env_config
+from oracle.ctf_oracle import OracleBatch, OracleEnv
+
+pytestmark = pytest.mark.gpu
+
+
+class HashPolicy(torch.nn.Module):
+    """Deterministic integer 'policy': the action is an exact hash of (observation, metadata, mask flag).
+
+    Exact in float64 on CPU and GPU alike, so the batched loops can be compared with per-env loops."""
+
+    def __init__(self, n_obs, n_meta, salt):
+        super().__init__()
+        g = torch.Generator().manual_seed(salt)
+        self.register_buffer("w1", torch.randint(1, 97, (n_obs,), generator=g).double())
+        self.register_buffer("w2", torch.randint(1, 97, (n_meta,), generator=g).double())
+
+    def _act(self, grid, meta, use_action_mask):
+        h = grid.double().flatten(1) @ self.w1 + (meta.double() * 64).round() @ self.w2
+        n = torch.where(use_action_mask.reshape(-1) == 1, 5, 9).double()
+        return (h - torch.floor(h / n) * n).long()
+
+    def get_action(self, grid, meta, use_action_mask):
+        return self._act(grid, meta, use_action_mask)
+
+    def get_action_and_value(self, grid, meta, use_action_mask, action=None):
+        a = self._act(grid, meta, use_action_mask)
+        return a, -a.float() / 8, torch.zeros_like(a, dtype=torch.float32), (a.float() * 0.5).unsqueeze(1)
+
+
+def _reference_style_rollout(ce, B, seed, agent, opponent, train_team1, T):
+    """ppo.py:31-131 per env on the oracle, with get_reversed_action applied on the host."""
+    orc = OracleBatch(ce, B, seed=seed)
+    orc.reset()  # the rollout starts with env.reset() (ppo.py:57): episode 1
+    N = ce.N_AGENTS
+    team = 0 if train_team1 else 1
+    mine = [i for i in range(N) if ce.AGENT_TEAMS[i] == team]
+    rev = [ce.cfg.reversed_action[a] for a in range(9)]
+    flags = torch.tensor([float(ce.AGENT_TYPE_ACTION_MASK[ce.AGENT_TYPES[i]]) for i in range(N)])
+    rec = {"actions": [], "rewards": [], "values": [], "grid": [], "meta": []}
+    for t in range(T):
+        obs, meta = orc.observe()
+        acts = np.zeros((B, N), dtype=np.uint8)
+        for i in range(N):
+            pol = agent if ce.AGENT_TEAMS[i] == team else opponent
+            a, _, _, v = pol.get_action_and_value(torch.from_numpy(obs[:, i]), torch.from_numpy(meta[:, i]), flags[i].expand(B))
+            if i in mine:
+                rec["actions"].append(a.numpy().copy())
+                rec["values"].append(v.reshape(B).numpy().copy())
+                rec["grid"].append(obs[:, i].copy())
+                rec["meta"].append(meta[:, i].copy())
+            a = a.numpy()
+            acts[:, i] = [rev[x] for x in a] if ce.AGENT_TEAMS[i] == 1 else a
+        r, d = orc.step(acts)
+        for i in mine:
+            rec["rewards"].append(r[:, i].copy())
+    obs, meta = orc.observe()
+    return {k: np.stack(v) for k, v in rec.items()}, obs[:, min(mine)], meta[:, min(mine)], d
+
+
+@pytest.mark.parametrize("train_team1", [True, False])
+def test_batched_rollout_matches_reference_loop(train_team1):
+    from marl_ctf_development_b200 import GridworldCtfGPU
+    from marl_ctf_development_b200.rollout import collect_rollout
+
+    exp, B, seed, T = "8_arena", 48, 9, 70
+    ec = experiment_env_config(exp)
+    env = GridworldCtfGPU(**ec, num_envs=B, device="cuda:0", seed=seed, reverse_team1_actions=True)
+    n_obs, n_meta = env.n_channels * env.GRID_SIZE**2, env.meta_size
+    agent, opponent = HashPolicy(n_obs, n_meta, 1), HashPolicy(n_obs, n_meta, 2)
+    ro = collect_rollout(env, agent.cuda(), opponent.cuda(), train_team1=train_team1, num_env_steps=T)
+    want, next_g, next_m, done = _reference_style_rollout(compiled(exp), B, seed, agent.cpu(), opponent.cpu(), train_team1, T)
+    assert np.array_equal(ro.actions.cpu().numpy(), want["actions"])
+    assert np.array_equal(bits(ro.rewards.cpu().numpy()), bits(want["rewards"]))
+    assert np.array_equal(ro.values.cpu().numpy(), want["values"])
+    assert np.array_equal(ro.grid_states.cpu().numpy(), want["grid"])
+    assert np.array_equal(bits(ro.metadata_states.cpu().numpy()), bits(want["meta"]))
+    assert np.array_equal(ro.next_grid_state.cpu().numpy(), next_g)
+    assert np.array_equal(bits(ro.next_metadata_state.cpu().numpy()), bits(next_m))
+    assert float(ro.dones.abs().sum()) == 0.0  # never written by the reference (ppo.py:53)
+    apt = env.N_AGENTS // 2
+    assert tuple(ro.grid_states.shape) == (T * apt, B, env.n_channels, env.GRID_SIZE, env.GRID_SIZE)
+
+
+def test_batched_duel_matches_reference_loop():
+    from marl_ctf_development_b200 import GridworldCtfGPU
+    from marl_ctf_development_b200.rollout import batched_duel
+
+    exp, B, seed, max_steps = "0_the_split", 64, 4, 90
+    ec = experiment_env_config(exp)
+    env = GridworldCtfGPU(**ec, num_envs=B, device="cuda:0", seed=seed, reverse_team1_actions=True, stats="counters")
+    ce = compiled(exp)
+    n_obs, n_meta = env.n_channels * env.GRID_SIZE**2, env.meta_size
+    agent, opponent = HashPolicy(n_obs, n_meta, 3), HashPolicy(n_obs, n_meta, 4)
+    result = batched_duel(env, agent.cuda(), opponent.cuda(), max_steps=max_steps)
+    # utils.duel on the oracle: reset, loop until done or step_count > max_steps
+    orc = OracleBatch(ce, B, seed=seed)
+    orc.reset()
+    N = ce.N_AGENTS
+    rev = [ce.cfg.reversed_action[a] for a in range(9)]
+    flags = torch.tensor([float(ce.AGENT_TYPE_ACTION_MASK[ce.AGENT_TYPES[i]]) for i in range(N)])
+    agent, opponent = agent.cpu(), opponent.cpu()
+    step_count, done = 0, False
+    while not done:
+        step_count += 1
+        obs, meta = orc.observe()
+        acts = np.zeros((B, N), dtype=np.uint8)
+        for i in range(N):
+            pol = agent if ce.AGENT_TEAMS[i] == 0 else opponent
+            a = pol.get_action(torch.from_numpy(obs[:, i]), torch.from_numpy(meta[:, i]), flags[i].expand(B)).numpy()
+            acts[:, i] = [rev[x] for x in a] if ce.AGENT_TEAMS[i] == 1 else a
+        _, d = orc.step(acts)
+        done = bool(d.all()) or step_count > max_steps
+    caps = orc.state()["captures"]
+    assert np.array_equal(result.cpu().numpy(), np.sign(caps[:, 0] - caps[:, 1]))
+    assert np.array_equal(env.stats_sum(all_reduce=False).cpu().numpy(), orc.state()["stats"].sum(0))
+
+
+def test_ctf_policy_in_the_rollout_respects_masks_and_shapes():
+    """BASELINE config 5 shape check: agent_network-style policy fed from the GPU env's buffers."""
+    from marl_ctf_development_b200 import GridworldCtfGPU
+    from marl_ctf_development_b200.policy import CtfPolicy
+    from marl_ctf_development_b200.rollout import collect_rollout
+
+    ec = experiment_env_config("8_arena")
+    B = 32
+    env = GridworldCtfGPU(**ec, num_envs=B, device="cuda:0", seed=1, reverse_team1_actions=True)
+    torch.manual_seed(0)
+    agent = CtfPolicy(9, env.n_channels, env.GRID_SIZE, env.meta_size).cuda()
+    opponent = CtfPolicy(9, env.n_channels, env.GRID_SIZE, env.meta_size).cuda()
+    ro = collect_rollout(env, agent, opponent, train_team1=True, num_env_steps=20, obs_storage_dtype=torch.uint8)
+    apt = 4
+    assert tuple(ro.actions.shape) == (20 * apt, B) and ro.grid_states.dtype == torch.uint8
+    masked_rows = ro.use_action_mask == 1  # guardians and scouts: only actions 0..4 (agent_network.py:66-75)
+    assert bool((ro.actions[masked_rows] <= 4).all()) and bool(masked_rows.any()) and bool((~masked_rows).any())
+    assert bool(torch.isfinite(ro.logprobs).all()) and bool(torch.isfinite(ro.values).all())
+
+
+# ---------------------------------------------------------------------------------------------------
+# single-env view with the reference's method surface
+# ---------------------------------------------------------------------------------------------------
+def test_single_env_view_replays_reference_trace_like_an_unmodified_caller():
+    from marl_ctf_development_b200 import GridworldCtf
+    from marl_ctf_development_b200.config import METRIC_NAMES
+
+    exp, kind, path = [t for t in golden_traces() if t[0] == "7_gridlocked" and t[1] == "seek"][0]
+    tr = np.load(path)
+    env = GridworldCtf(**experiment_env_config(exp), seed=int(tr["seed"]), env_id=int(tr["env_id"]))
+    assert env.get_env_dims() == ((13, 13, 13), (12, 13, 13), (18,), (87,))
+    oi = 1
+    T = int(tr["episode_lengths"][0])
+    for t in range(T):
+        grid, rewards, done = env.step([int(a) for a in tr["actions"][t]])   # list in, (grid, list, bool) out
+        assert isinstance(rewards, list) and isinstance(done, bool)
+        assert np.array_equal(grid, tr["grid"][t])
+        assert np.array_equal(bits(np.array(rewards, dtype=np.float32)), bits(tr["rewards"][t]))
+        assert done == bool(tr["done"][t])
+        if t % 50 == 0:
+            assert env.agent_positions == {i: tuple(int(x) for x in tr["pos"][t][i]) for i in range(env.N_AGENTS)}
+            assert np.array_equal(env.has_flag, tr["has_flag"][t])
+            assert [env.agent_hp[i] * 4 for i in range(env.N_AGENTS)] == tr["hp_q"][t].tolist()
+        if traces.snap_after_step(t + 1, env.env_step_count, env.GAME_STEPS):
+            assert tr["obs_steps"][oi] == t + 1
+            for i in range(env.N_AGENTS):
+                o = env.standardise_state(i, reverse_grid=(env.AGENT_TEAMS[i] != 0))
+                assert o.dtype == np.uint8 and o.shape == (1, 13, 13, 13)
+                assert np.array_equal(o[0], tr["obs"][oi][i])
+                m = env.get_env_metadata(i)
+                assert m.dtype == np.float16 and np.array_equal(m[0].astype(np.float32), tr["meta"][oi][i])
+            oi += 1
+    metrics = env.metrics
+    for k, name in enumerate(METRIC_NAMES):
+        for i in range(env.N_AGENTS):
+            assert metrics["agent_" + name][i] == tr["stats"][0][k, i]
+    assert metrics["team_flag_captures"][0] == tr["captures"][T - 1][0]
+    assert np.array_equal(np.stack([metrics["agent_visitation_maps"][i] for i in range(env.N_AGENTS)]), tr["visits"][0])
+    with pytest.raises(KeyError):
+        env.step([9] * env.N_AGENTS)
+    env.reset()
+    assert env.env_step_count == 0 and not env.done
+
+
+def test_single_env_view_symmetry_assert_and_reversed_actions():
+    from marl_ctf_development_b200 import GridworldCtf
+
+    env = GridworldCtf(**experiment_env_config("8_arena"))  # MAP_SYMMETRY_CHECK=True runs in the ctor (:476-477)
+    assert np.array_equal(env.standardise_state(0), env.standardise_state(1, reverse_grid=True))
+    assert [env.get_reversed_action(a) for a in range(9)] == [1, 0, 3, 2, 4, 6, 5, 8, 7]
+    orc = OracleEnv(compiled("8_arena"))
+    for i in range(8):
+        for rev in (False, True):
+            assert np.array_equal(env.standardise_state(i, reverse_grid=rev), orc.standardise_state(i, reverse_grid=rev))
