@@ -74,11 +74,20 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.environ.get("CTF_B200_LIB"):
+        # a fresh checkout has no .so (built artefacts are git-ignored): compile it in-tree with nvcc
+        from .build import build_native
+
+        try:
+            build_native()
+        except Exception as exc:
+            if not os.path.exists(LIB_PATH):
+                raise NativeError(
+                    f"{LIB_PATH} is missing and could not be built ({exc}). "
+                    "The step path is CUDA-only: there is no CPU fallback."
+                ) from exc
     if not os.path.exists(LIB_PATH):
-        raise NativeError(
-            f"{LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "or `python -m marl_ctf_development_b200.build`. The step path is CUDA-only: there is no CPU fallback."
-        )
+        raise NativeError(f"{LIB_PATH} not found. The step path is CUDA-only: there is no CPU fallback.")
     L = C.CDLL(LIB_PATH)
     for sym in EXPORTS:
         if not hasattr(L, sym):

@@ -423,6 +423,44 @@ void ctf_oracle_metadata(const ctf_oracle_env_t* e, int agent, float* out /* [6+
     for (int i = 0; i < M; ++i) out[i] = ctf_oracle_f64_to_f16_to_f32(m[i]); /* :1044 float16 store, ppo.py:70 */
 }
 
+/* Same result as ctf_oracle_standardise_state + float cast, written the way an optimised CPU port would
+ * (zero the block, then set one element per non-open cell and the self plane).  Used only by the timed CPU
+ * baseline legs so that the reported baseline is not handicapped; tests/test_oracle_golden.py checks it
+ * against the literal restatement above. */
+void ctf_oracle_standardise_state_f32_fast(const ctf_oracle_env_t* e, int agent, int reverse_grid, float* out) {
+    const ctf_config_t* c = e->cfg;
+    const int G = c->grid_size, GG = G * G;
+    const int team = c->agent_team[agent];
+    memset(out, 0, sizeof(float) * (size_t)c->n_channels * GG);
+    for (int r = 0; r < G; ++r)
+        for (int cc = 0; cc < G; ++cc) {
+            const int t = e->grid[r * G + cc];
+            const int self = (r == e->row[agent] && cc == e->col[agent]);
+            if (t == 0 && !self) continue;
+            int dr = r, dc = cc;
+            if (reverse_grid) {
+                switch (c->flip_axis) {
+                    case -1: dr = G - 1 - r; dc = G - 1 - cc; break;
+                    case 0:  dr = G - 1 - r; break;
+                    case 1:  dc = G - 1 - cc; break;
+                    default: dr = G - 1 - cc; dc = G - 1 - r; break;
+                }
+            }
+            const int ch = c->chan_lut[team][t & 15];
+            if (ch) out[ch * GG + dr * G + dc] = 1.0f;
+            if (self) out[dr * G + dc] = 1.0f;
+        }
+}
+
+void ctf_oracle_observe_fast(const ctf_oracle_env_t* e, float* obs, float* meta) {
+    const ctf_config_t* c = e->cfg;
+    const int per_agent = c->n_channels * c->grid_size * c->grid_size, M = 6 + 2 * c->n_agents;
+    for (int a = 0; a < c->n_agents; ++a) {
+        ctf_oracle_standardise_state_f32_fast(e, a, c->obs_reverse[a], obs + (size_t)a * per_agent);
+        ctf_oracle_metadata(e, a, meta + a * M);
+    }
+}
+
 /* observations for all agents as the callers build them (ppo.py:66-95, utils.py:528-551) */
 void ctf_oracle_observe(const ctf_oracle_env_t* e, const uint8_t* reverse_flags, float* obs, uint8_t* obs_u8, float* meta) {
     const ctf_config_t* c = e->cfg;
@@ -633,7 +671,7 @@ static void* batch_run_worker(void* arg) {
         for (int t = 0; t < job->steps; ++t) {
             if (done) ctf_oracle_reset(e);
             if (job->with_obs) {
-                ctf_oracle_observe(e, NULL, obs, NULL, meta);
+                ctf_oracle_observe_fast(e, obs, meta);
                 checksum += obs[(size_t)(t * 7919) % per_env_obs] + meta[0];
             }
             uint64_t r = splitmix64(&s);

@@ -61,6 +61,7 @@ def lib():
         L.ctf_oracle_batch_set_state.argtypes = [C.c_void_p] * 7
         L.ctf_oracle_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int]
         L.ctf_oracle_batch_run.restype = C.c_double
+        L.ctf_oracle_observe_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -101,6 +102,13 @@ class OracleEnv:
         self.L.ctf_oracle_observe(
             self._e, None if rf is None else _p(rf), None if u8 else _p(obs), _p(obs) if u8 else None, _p(meta)
         )
+        return obs, meta
+
+    def observe_fast(self):
+        """The baseline legs' observation writer (must equal observe())."""
+        obs = np.full((self.N, self.Cn, self.G, self.G), 7.0, dtype=np.float32)
+        meta = np.zeros((self.N, self.M), dtype=np.float32)
+        self.L.ctf_oracle_observe_fast(self._e, _p(obs), _p(meta))
         return obs, meta
 
     def standardise_state(self, agent_idx, reverse_grid=False):

@@ -198,3 +198,49 @@ def test_single_env_view_symmetry_assert_and_reversed_actions():
     for i in range(8):
         for rev in (False, True):
             assert np.array_equal(env.standardise_state(i, reverse_grid=rev), orc.standardise_state(i, reverse_grid=rev))
+
+
+def test_json_trace_export_matches_reference_wire_format(tmp_path):
+    """utils.duel_json (utils.py:728-814): same keys / coordinate convention; content equals the same duel on the oracle."""
+    import json
+
+    from marl_ctf_development_b200 import GridworldCtfGPU
+    from marl_ctf_development_b200.trace_export import duel_json
+
+    exp, B, seed, idx, max_steps = "7_gridlocked", 8, 6, 3, 150
+    env = GridworldCtfGPU(**experiment_env_config(exp), num_envs=B, device="cuda:0", seed=seed, reverse_team1_actions=True)
+    ce = compiled(exp)
+    n_obs, n_meta = env.n_channels * env.GRID_SIZE**2, env.meta_size
+    agent, opponent = HashPolicy(n_obs, n_meta, 5), HashPolicy(n_obs, n_meta, 6)
+    path = tmp_path / "trace.json"
+    duel_json(env, agent.cuda(), opponent.cuda(), env_index=idx, max_steps=max_steps, fname=str(path))
+    d = json.loads(path.read_text())
+    assert list(d) == ["grid_size", "flag_pos", "spawn_pos", "agent_config", "block_tiles", "destructible_tiles", "movement", "tiles", "scores"]
+    assert len(d["movement"]) == max_steps + 1 == len(d["tiles"]) == len(d["scores"])  # 151 steps, like json/*.json
+    assert d["flag_pos"]["0"] == {"x": ce.FLAG_POSITIONS[0][1], "z": ce.FLAG_POSITIONS[0][0]}
+    # the same duel on the oracle, env `idx` only
+    orc = OracleBatch(ce, 1, seed=seed, env_id_base=idx)
+    orc.reset()
+    N = ce.N_AGENTS
+    rev = [ce.cfg.reversed_action[a] for a in range(9)]
+    flags = torch.tensor([float(ce.AGENT_TYPE_ACTION_MASK[ce.AGENT_TYPES[i]]) for i in range(N)])
+    agent, opponent = agent.cpu(), opponent.cpu()
+    g0 = orc.state()["grid"][0]
+    assert d["block_tiles"] == [{"x": int(x), "z": int(z)} for z, x in zip(*np.where(g0 == 1))]
+    pos = orc.state()["pos"][0].astype(int)
+    for t in range(max_steps + 1):
+        obs, meta = orc.observe()
+        acts = np.zeros((1, N), dtype=np.uint8)
+        for i in range(N):
+            pol = agent if ce.AGENT_TEAMS[i] == 0 else opponent
+            a = int(pol.get_action(torch.from_numpy(obs[:, i]), torch.from_numpy(meta[:, i]), flags[i].expand(1))[0])
+            acts[0, i] = rev[a] if ce.AGENT_TEAMS[i] == 1 else a
+        orc.step(acts)
+        st = orc.state()
+        new = st["pos"][0].astype(int)
+        want = [{"x": int(new[i, 1] - pos[i, 1]), "z": int(new[i, 0] - pos[i, 0]), "has_flag": int(st["has_flag"][0][i])} for i in range(N)]
+        assert d["movement"][t] == want, t
+        assert d["scores"][t] == [{"t0": int(st["captures"][0][0]), "t1": int(st["captures"][0][1])}]
+        g = st["grid"][0]
+        assert len(d["tiles"][t]) == int(((g == 2) | (g == 3)).sum())
+        pos = new

@@ -43,6 +43,8 @@ def _check_obs(env, tr, i, where):
     assert np.array_equal(bits(meta), bits(tr["meta"][i])), where + " meta"
     obs8, _ = env.observe(u8=True)
     assert np.array_equal(obs8, tr["obs"][i]), where + " obs u8"
+    obs_f, meta_f = env.observe_fast()  # the CPU-baseline writer gives the same bytes
+    assert np.array_equal(obs_f, obs) and np.array_equal(bits(meta_f), bits(meta)), where + " fast writer"
 
 
 def test_half_rounding_matches_numpy():
