@@ -671,7 +671,10 @@ static void* batch_run_worker(void* arg) {
         for (int t = 0; t < job->steps; ++t) {
             if (done) ctf_oracle_reset(e);
             if (job->with_obs) {
-                ctf_oracle_observe_fast(e, obs, meta);
+                /* 1: the literal restatement of standardise_state (compare planes, then flip);
+                   2: the tuned writer (same bytes, scatter of the non-open cells) */
+                if (job->with_obs == 2) ctf_oracle_observe_fast(e, obs, meta);
+                else ctf_oracle_observe(e, NULL, obs, NULL, meta);
                 checksum += obs[(size_t)(t * 7919) % per_env_obs] + meta[0];
             }
             uint64_t r = splitmix64(&s);

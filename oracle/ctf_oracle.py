@@ -192,8 +192,11 @@ class OracleBatch:
         )
         return obs, meta
 
-    def run(self, steps: int, seed: int, with_obs: bool, n_threads: int) -> float:
-        """Threaded continuation with uniform random actions (CPU legs of bench.py). Returns a checksum."""
+    def run(self, steps: int, seed: int, with_obs, n_threads: int) -> float:
+        """Threaded continuation with uniform random actions (CPU legs of bench.py). Returns a checksum.
+
+        with_obs: 0 = step() only; 1 / True = observations through the literal restatement of the reference's
+        standardise_state; 2 = through the tuned writer (same bytes)."""
         return float(self.L.ctf_oracle_batch_run(self._h, int(steps), int(seed), int(with_obs), int(n_threads)))
 
     def state(self) -> dict:
