@@ -206,7 +206,7 @@ def run_ours(args) -> dict | None:
     ec = experiment_env_config(EXPERIMENT)
     env = GridworldCtfGPU(**ec, num_envs=B, device=dev, seed=args.seed, env_id_base=rank * B,
                           stats="none" if args.no_stats else "counters",
-                          obs_dtype=torch.float32 if args.obs_dtype == "float32" else torch.uint8)
+                          obs_dtype=getattr(torch, args.obs_dtype))
     N, G, C = env.N_AGENTS, env.GRID_SIZE, env.n_channels
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 8  # distinct pre-generated action tensors, resident in HBM before the timed region
@@ -277,7 +277,7 @@ def run_ours(args) -> dict | None:
     if rank == 0:
         agent_steps = world * B * N * K
         value = agent_steps / (ms * 1e-3)
-        per_agent_step = algorithmic_bytes_per_agent_step(G, N, C, 4 if args.obs_dtype == "float32" else 1)
+        per_agent_step = algorithmic_bytes_per_agent_step(G, N, C, {"float32": 4, "uint8": 1}.get(args.obs_dtype, 2))
         launch_s = ms * 1e-3 / K
         achieved = per_agent_step * B * N / launch_s / 1e9
         peak, peak_src = measured_hbm_peak()
@@ -297,7 +297,7 @@ def run_ours(args) -> dict | None:
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["bytes_per_launch"] if traffic and traffic.get("envs_per_gpu") == B else None,
-                "kernel": "k_step<%s,%s>" % ("float" if args.obs_dtype == "float32" else "uint8_t", "false" if args.no_stats else "true"),
+                "kernel": "k_step<%s,%s>" % ({"float32": "float", "uint8": "uint8_t", "float16": "__half", "bfloat16": "__nv_bfloat16"}[args.obs_dtype], "false" if args.no_stats else "true"),
                 "algorithmic_bytes_per_agent_step": per_agent_step,
                 "bytes_per_launch": per_agent_step * B * N,
                 "launch_ms": launch_s * 1e3,
@@ -323,8 +323,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-stats", action="store_true", help="skip the episode-statistics counters")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--obs-dtype", choices=["float32", "uint8"], default="float32",
-                    help="float32 is the drop-in default and the headline; uint8 is reported separately")
+    ap.add_argument("--obs-dtype", choices=["float32", "uint8", "float16", "bfloat16"], default="float32",
+                    help="float32 is the drop-in default and the headline; the narrower buffers are reported separately")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 

@@ -63,7 +63,8 @@ enum ctf_error {
     CTF_ERR_NO_DEVICE = -3
 };
 
-enum ctf_obs_dtype { CTF_OBS_F32 = 0, CTF_OBS_U8 = 1 };
+/* element type of the observation buffer; the values are {0, 1}, exact in every type */
+enum ctf_obs_dtype { CTF_OBS_F32 = 0, CTF_OBS_U8 = 1, CTF_OBS_F16 = 2, CTF_OBS_BF16 = 3 };
 
 /*
  * Compiled environment description: everything GridworldCtf.__init__ +
@@ -135,7 +136,7 @@ typedef struct ctf_state {
 
 /* Device output buffers of one reset()/step(). Any pointer may be NULL to skip that output. */
 typedef struct ctf_outputs {
-    void* obs;        /* [B][N][C][G][G] float32 (or uint8): standardise_state(i, obs_reverse[i]) for every agent */
+    void* obs;        /* [B][N][C][G][G] float32 (or uint8 / float16 / bfloat16): standardise_state(i, obs_reverse[i]) for every agent */
     float* meta;      /* [B][N][6+2N] float32: get_env_metadata(i) (fp16-rounded values) */
     float* rewards;   /* [B][N] float32 */
     uint8_t* dones;   /* [B] 0/1 */

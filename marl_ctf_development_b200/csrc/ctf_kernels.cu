@@ -14,6 +14,7 @@
 // Randomness is Philox4x32-10 addressed by (seed, global env id, episode, step,
 // site); see marl_ctf_development_b200/draws.py for the site map.  Lane l of the
 // warp generates site l.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -160,6 +161,30 @@ __device__ __forceinline__ uint4 expand_bits<uint8_t>(uint32_t b) {  // 16 eleme
     return v;
 }
 
+// 8 elements of a 16-bit float type whose 1.0 is ONE: word k packs bits 2k (low half) and 2k+1 (high half)
+template <uint32_t ONE>
+__device__ __forceinline__ uint4 expand_bits16(uint32_t b) {
+    uint4 v;
+    v.x = (((b & 3u) * 0x8001u) & 0x10001u) * ONE;
+    v.y = ((((b >> 2) & 3u) * 0x8001u) & 0x10001u) * ONE;
+    v.z = ((((b >> 4) & 3u) * 0x8001u) & 0x10001u) * ONE;
+    v.w = ((((b >> 6) & 3u) * 0x8001u) & 0x10001u) * ONE;
+    return v;
+}
+template <>
+__device__ __forceinline__ uint4 expand_bits<__half>(uint32_t b) { return expand_bits16<0x3C00u>(b); }
+template <>
+__device__ __forceinline__ uint4 expand_bits<__nv_bfloat16>(uint32_t b) { return expand_bits16<0x3F80u>(b); }
+
+template <typename T>
+__device__ __forceinline__ T from_bit(uint32_t bit) { return (T)bit; }
+template <>
+__device__ __forceinline__ __half from_bit<__half>(uint32_t bit) { return __ushort_as_half((unsigned short)(bit ? 0x3C00u : 0u)); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_bit<__nv_bfloat16>(uint32_t bit) {
+    return __ushort_as_bfloat16((unsigned short)(bit ? 0x3F80u : 0u));
+}
+
 template <typename T>
 __device__ __forceinline__ void write_obs(const DevPlan& P, const WarpMem& w, uint32_t me, uint32_t rev_mask,
                                           T* __restrict__ obs_env, int lane) {
@@ -217,10 +242,10 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const WarpMem& w, ui
     const int head = mis ? min(VEC - (int)mis, E) : 0;
     const int nvec = (E - head) / VEC;
     const int tail = E - head - nvec * VEC;
-    if (lane < head) obs_env[lane] = (T)((w.bits[lane >> 5] >> (lane & 31)) & 1u);
+    if (lane < head) obs_env[lane] = from_bit<T>((w.bits[lane >> 5] >> (lane & 31)) & 1u);
     if (lane < tail) {
         const int e = head + nvec * VEC + lane;
-        obs_env[e] = (T)((w.bits[e >> 5] >> (e & 31)) & 1u);
+        obs_env[e] = from_bit<T>((w.bits[e >> 5] >> (e & 31)) & 1u);
     }
     uint4* __restrict__ vp = reinterpret_cast<uint4*>(obs_env + head);
     if ((head & (VEC - 1)) == 0 && sizeof(T) == 4) {
@@ -670,7 +695,7 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
     if (c.n_channels < 1 || c.n_channels > CTF_MAX_CHANNELS) return fail(CTF_ERR_INVALID, "n_channels out of range");
     if (c.flip_axis < -1 || c.flip_axis > 2) return fail(CTF_ERR_INVALID, "flip_axis must be -1, 0, 1 or 2");
     if (c.game_steps < 1) return fail(CTF_ERR_INVALID, "game_steps must be positive");
-    if (obs_dtype != CTF_OBS_F32 && obs_dtype != CTF_OBS_U8) return fail(CTF_ERR_INVALID, "unknown obs dtype");
+    if (obs_dtype < CTF_OBS_F32 || obs_dtype > CTF_OBS_BF16) return fail(CTF_ERR_INVALID, "unknown obs dtype");
     const int G = c.grid_size, N = c.n_agents;
     P.tag_threshold = c.tag_threshold;
     P.reward_step = c.reward_step; P.reward_capture = c.reward_capture; P.reward_tag = c.reward_tag;
@@ -780,11 +805,11 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
     if (e == cudaSuccess) e = cudaMalloc(&h->dones_stage, (size_t)num_envs);
     const int smem = (int)h->smem_bytes;
 #define CTF_SET_SMEM(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-    CTF_SET_SMEM((k_step<float, false>)); CTF_SET_SMEM((k_step<float, true>));
-    CTF_SET_SMEM((k_step<uint8_t, false>)); CTF_SET_SMEM((k_step<uint8_t, true>));
-    CTF_SET_SMEM((k_reset<float, false>)); CTF_SET_SMEM((k_reset<float, true>));
-    CTF_SET_SMEM((k_reset<uint8_t, false>)); CTF_SET_SMEM((k_reset<uint8_t, true>));
-    CTF_SET_SMEM((k_observe<float>)); CTF_SET_SMEM((k_observe<uint8_t>));
+#define CTF_SET_SMEM_T(T)                                                                                    \
+    CTF_SET_SMEM((k_step<T, false>)); CTF_SET_SMEM((k_step<T, true>)); CTF_SET_SMEM((k_reset<T, false>)); \
+    CTF_SET_SMEM((k_reset<T, true>)); CTF_SET_SMEM((k_observe<T>))
+    CTF_SET_SMEM_T(float); CTF_SET_SMEM_T(uint8_t); CTF_SET_SMEM_T(__half); CTF_SET_SMEM_T(__nv_bfloat16);
+#undef CTF_SET_SMEM_T
 #undef CTF_SET_SMEM
     if (e != cudaSuccess) {
         fail(CTF_ERR_CUDA, "ctf_create: %s", cudaGetErrorString(e));
@@ -807,7 +832,7 @@ extern "C" int ctf_destroy(ctf_handle_t h) {
 extern "C" int ctf_get_sizes(ctf_handle_t h, ctf_sizes_t* s) {
     if (!h || !s) return fail(CTF_ERR_INVALID, "null argument");
     const DevPlan& P = h->plan;
-    const size_t B = (size_t)h->B, elem = h->obs_dtype == CTF_OBS_F32 ? 4 : 1;
+    const size_t B = (size_t)h->B, elem = h->obs_dtype == CTF_OBS_F32 ? 4 : (h->obs_dtype == CTF_OBS_U8 ? 1 : 2);
     s->grid_stride = kGridBytes;
     s->grid_bytes = B * kGridBytes;
     s->agents_bytes = B * P.N * 8;
@@ -844,6 +869,17 @@ static int make_launch(ctf_handle_t h, const ctf_state_t& st, const ctf_outputs_
 
 static unsigned grid_dim(long long B) { return (unsigned)((B + kWarpsPerCta - 1) / kWarpsPerCta); }
 
+// calls f(T{}) with the observation element type of the handle
+template <typename F>
+static void with_obs_type(int obs_dtype, F&& f) {
+    switch (obs_dtype) {
+        case CTF_OBS_F32: f(float{}); break;
+        case CTF_OBS_U8: f(uint8_t{}); break;
+        case CTF_OBS_F16: f(__half{}); break;
+        default: f(__nv_bfloat16{}); break;
+    }
+}
+
 extern "C" int ctf_reset(ctf_handle_t h, ctf_state_t st, ctf_outputs_t out, int first, void* stream) {
     if (!h) return fail(CTF_ERR_INVALID, "null handle");
     Launch L;
@@ -852,21 +888,23 @@ extern "C" int ctf_reset(ctf_handle_t h, ctf_state_t st, ctf_outputs_t out, int 
     L.first_reset = first ? 1 : 0;
     CTF_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool f32 = h->obs_dtype == CTF_OBS_F32, stats = h->stats_level > 0;
-    if (f32 && stats) k_reset<float, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-    else if (f32) k_reset<float, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-    else if (stats) k_reset<uint8_t, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-    else k_reset<uint8_t, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+    const bool stats = h->stats_level > 0;
+    with_obs_type(h->obs_dtype, [&](auto tag) {
+        using T = decltype(tag);
+        if (stats) k_reset<T, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+        else k_reset<T, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+    });
     CTF_CUDA(cudaGetLastError());
     return CTF_OK;
 }
 
 static int launch_step(ctf_handle_t h, const Launch& L, cudaStream_t s) {
-    const bool f32 = h->obs_dtype == CTF_OBS_F32, stats = h->stats_level > 0;
-    if (f32 && stats) k_step<float, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-    else if (f32) k_step<float, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-    else if (stats) k_step<uint8_t, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-    else k_step<uint8_t, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+    const bool stats = h->stats_level > 0;
+    with_obs_type(h->obs_dtype, [&](auto tag) {
+        using T = decltype(tag);
+        if (stats) k_step<T, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+        else k_step<T, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+    });
     CTF_CUDA(cudaGetLastError());
     return CTF_OK;
 }
@@ -894,8 +932,9 @@ extern "C" int ctf_observe(ctf_handle_t h, ctf_state_t st, const uint8_t* revers
     }
     CTF_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (h->obs_dtype == CTF_OBS_F32) k_observe<float><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-    else k_observe<uint8_t><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+    with_obs_type(h->obs_dtype, [&](auto tag) {
+        k_observe<decltype(tag)><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+    });
     CTF_CUDA(cudaGetLastError());
     return CTF_OK;
 }

@@ -25,7 +25,7 @@ from .config import METRIC_NAMES, N_METRICS, compile_config, env_dims
 from .sharding import all_reduce_stats
 
 _STATS_LEVELS = {"none": 0, "counters": 1, "full": 2}
-_OBS_DTYPES = {torch.float32: 0, torch.uint8: 1}
+_OBS_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.float16: 2, torch.bfloat16: 3}
 _GRID_ROW = 16
 
 
@@ -102,7 +102,7 @@ class GridworldCtfGPU:
         if stats not in _STATS_LEVELS:
             raise ValueError(f"stats must be one of {list(_STATS_LEVELS)}")
         if obs_dtype not in _OBS_DTYPES:
-            raise ValueError("obs_dtype must be torch.float32 or torch.uint8")
+            raise ValueError("obs_dtype must be torch.float32, torch.uint8, torch.float16 or torch.bfloat16")
         self.stats_level = _STATS_LEVELS[stats]
         self.obs_dtype = obs_dtype
         self.seed = int(seed)

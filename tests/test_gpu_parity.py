@@ -11,6 +11,7 @@ import traces
 from helpers import STATE_KEYS, bits, compiled, golden_ids, golden_traces
 from marl_ctf_development_b200 import experiment_env_config
 from oracle.ctf_oracle import OracleBatch
+from kwarg_cases import CASE_IDS, KWARG_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -34,7 +35,8 @@ def _assert_batch_state(env, orc, where, keys=STATE_KEYS + ("step", "episode")):
 
 def _assert_obs(env, orc, where, u8=False):
     o_ref, m_ref = orc.observe(u8=u8)
-    assert np.array_equal(env.obs.cpu().numpy(), o_ref), where + ": observations differ"
+    got = env.obs if env.obs.dtype in (torch.float32, torch.uint8) else env.obs.float()  # {0,1} are exact in fp16/bf16
+    assert np.array_equal(got.cpu().numpy(), o_ref), where + ": observations differ"
     assert np.array_equal(bits(env.meta.cpu().numpy()), bits(m_ref)), where + ": metadata differs"
 
 
@@ -141,9 +143,24 @@ def test_uint8_observations_all_alignments():
     _run_against_oracle("8_arena", 33, 60, "seek", seed=18, obs_every=10, obs_dtype=torch.uint8)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_observation_buffers(dtype):
+    """fp16 / bf16 policy input buffers: same {0,1} planes, 8 elements per 128-bit store, every alignment phase."""
+    _run_against_oracle("7_gridlocked", 67, 40, "builder", seed=24, obs_every=8, obs_dtype=dtype)
+    _run_against_oracle("8_arena", 130, 40, "seek", seed=25, obs_every=8, obs_dtype=dtype)
+    _run_against_oracle("0_the_split", 9, 40, "seek", seed=26, obs_every=8, obs_dtype=dtype, stats="full")
+
+
 @pytest.mark.parametrize("exp", ["1_fence", "2_jailbreak", "3_one_way_out", "4_keyhole", "5_skittles", "6_the_wall"])
 def test_other_experiments_against_oracle(exp):
     _run_against_oracle(exp, 128, 260, "builder", seed=19, obs_every=20, stats="full")
+
+
+@pytest.mark.parametrize("name,exp,overrides,kind", KWARG_CASES, ids=CASE_IDS)
+def test_constructor_keyword_variations(name, exp, overrides, kind):
+    """The ctor keywords / team layouts pinned against the reference in test_oracle_vs_reference.py, on the GPU."""
+    steps = min(experiment_env_config(exp)["GAME_STEPS"] if "GAME_STEPS" not in overrides else overrides["GAME_STEPS"], 240) + 2
+    _run_against_oracle(exp, 96, steps, kind, seed=23, obs_every=15, stats="full", env_overrides=dict(overrides))
 
 
 def test_no_stats_variant_matches():

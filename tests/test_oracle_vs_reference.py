@@ -11,6 +11,7 @@ from helpers import STATE_KEYS, assert_state_equal, bits
 from marl_ctf_development_b200.config import compile_config, env_dims
 from oracle import ref_shim as rs
 from oracle.ctf_oracle import OracleEnv
+from kwarg_cases import CASE_IDS, KWARG_CASES, build_env_config
 
 pytestmark = [
     pytest.mark.reference,
@@ -101,3 +102,36 @@ def test_all_flip_axes_are_covered(exp, flip):
         assert np.array_equal(ref.standardise_state(i, reverse_grid=True), orc.standardise_state(i, reverse_grid=True))
     for a in range(9):
         assert ref.get_reversed_action(a) == ce.cfg.reversed_action[a]
+
+
+@pytest.mark.parametrize("name,exp,overrides,kind", KWARG_CASES, ids=CASE_IDS)
+def test_constructor_keyword_variations(name, exp, overrides, kind):
+    """Every ctor keyword the step path reads (gridworld_ctf.py:19-52), odd team layouts, other HP grids."""
+    ec = build_env_config(rs.experiment_env_config(exp), overrides)
+    ce = compile_config(**ec)
+    seed, env_id = 4242, 17
+    ref = rs.make_injected_env(ec, seed=seed, env_id=env_id)
+    orc = OracleEnv(ce, seed=seed, env_id=env_id)
+    assert env_dims(ce) == ref.get_env_dims()
+    assert [int(t) for t in ce.TILES_USED] == [int(t) for t in ref.TILES_USED]
+    assert ce.OPPONENTS == ref.OPPONENTS
+    pol = traces.make_policy(kind, ce)
+    rng = np.random.default_rng(11)
+    steps = min(ec["GAME_STEPS"] + 2, 300)
+    for t in range(steps):
+        s = rs.snapshot(ref, ce.cfg.hp_scale)
+        a = pol(rng, s["pos"], s["has_flag"])
+        _, rr, rd = ref.step(a.tolist())
+        orr, od = orc.step(a)
+        assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"{name} t={t}")
+        assert rd == od
+        assert np.array_equal(bits(np.array(rr, dtype=np.float32)), bits(orr)), (name, t, rr, orr)
+        if t % 7 == 0 or t == steps - 1:
+            ro, rm = rs.observations(ref)
+            oo, om = orc.observe()
+            assert np.array_equal(ro, oo), (name, t)
+            assert np.array_equal(bits(rm), bits(om)), (name, t, rm, om)
+    st = orc.state()
+    assert np.array_equal(rs.agent_metrics(ref), st["stats"])
+    vm = np.stack([ref.metrics["agent_visitation_maps"][i] for i in range(ce.N_AGENTS)])
+    assert np.array_equal(vm, st["visits"])
