@@ -244,3 +244,68 @@ def test_json_trace_export_matches_reference_wire_format(tmp_path):
         g = st["grid"][0]
         assert len(d["tiles"][t]) == int(((g == 2) | (g == 3)).sum())
         pos = new
+
+
+def test_league_duel_batches_match_per_pair_duels():
+    """N3: all (agent, opponent) pairs of a win-rate matrix in one env batch == one utils.duel per pair on the oracle."""
+    from marl_ctf_development_b200.league import duel_pairs, winrate_matrix_non_symmetric
+
+    exp, D, seed, max_steps = "0_the_split", 6, 8, 60
+    ec = experiment_env_config(exp)
+    ce = compiled(exp)
+    n_obs, n_meta = ce.n_channels * ce.GRID_SIZE**2, ce.meta_size
+    t1 = [HashPolicy(n_obs, n_meta, 10 + i) for i in range(2)]
+    t2 = [HashPolicy(n_obs, n_meta, 20 + i) for i in range(2)]
+    pairs = [(a, o) for a in t1 for o in t2]
+    results, metrics = duel_pairs(ec, [(a.cuda(), o.cuda()) for a, o in pairs], D, max_steps=max_steps, device="cuda:0", seed=seed, collect_metrics=True)
+    N = ce.N_AGENTS
+    rev = [ce.cfg.reversed_action[a] for a in range(9)]
+    flags = torch.tensor([float(ce.AGENT_TYPE_ACTION_MASK[ce.AGENT_TYPES[i]]) for i in range(N)])
+    for p, (agent, opponent) in enumerate(pairs):
+        agent, opponent = agent.cpu(), opponent.cpu()
+        orc = OracleBatch(ce, D, seed=seed, env_id_base=p * D)
+        orc.reset()
+        for step in range(max_steps + 1):
+            obs, meta = orc.observe()
+            acts = np.zeros((D, N), dtype=np.uint8)
+            for i in range(N):
+                pol = agent if ce.AGENT_TEAMS[i] == 0 else opponent
+                a = pol.get_action(torch.from_numpy(obs[:, i]), torch.from_numpy(meta[:, i]), flags[i].expand(D)).numpy()
+                acts[:, i] = [rev[x] for x in a] if ce.AGENT_TEAMS[i] == 1 else a
+            orc.step(acts)
+        so = orc.state()
+        assert np.array_equal(results[p].cpu().numpy(), np.sign(so["captures"][:, 0] - so["captures"][:, 1]))
+        want = so["stats"].sum(0)
+        for k, name in enumerate(["tag_count", "respawn_tag_count", "flag_pickups", "flag_captures"]):
+            for i in range(N):
+                assert metrics[p]["agent_" + name][i] == want[k, i]
+    wm = winrate_matrix_non_symmetric(ec, [a.cuda() for a in t1], [o.cuda() for o in t2], D, max_steps=max_steps, device="cuda:0", seed=seed)
+    assert set(wm) == {(f"0_{i}", f"1_{j}") for i in range(2) for j in range(2)} | {(f"1_{j}", f"0_{i}") for i in range(2) for j in range(2)}
+    r = results.cpu().numpy()
+    assert abs(wm[("0_1", "1_0")] - (r[2] == 1).mean()) < 1e-12
+    assert abs(wm[("1_0", "0_1")] - (r[2] == -1).mean()) < 1e-12
+
+
+def test_bench_contract_keys():
+    """bench.py prints one JSON line with the keys the driver reads (small sizes here; the real run uses the defaults)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    proc = subprocess.run(
+        [sys.executable, os.path.join(root, "bench.py"), "--steps", "6", "--warmup", "3", "--envs", "2048", "--no-cpu-baseline"],
+        capture_output=True, text=True, timeout=600, cwd=root,
+    )
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in d, key
+    assert d["metric"] == "agent_steps_per_sec" and d["steps"] == 6 and d["gpu_launches"] >= 6 and d["value"] > 0
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 2048 * 8
+    assert "workload" in d["config"] and "model" not in d["config"]
