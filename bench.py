@@ -291,7 +291,7 @@ def run_ours(args) -> dict | None:
             "e2e": {
                 "value": world * B * N * Ke / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": B * N, "d2h_bytes_per_step": B * N * 4 + B,
-                "steps": Ke, "api": "GridworldCtfGPU.step_host -> ctf_step_host (pinned host actions in, rewards+dones out; obs/meta stay in HBM)",
+                "steps": Ke, "api": "GridworldCtfGPU.step_host -> ctf_step_host (pinned host actions in, rewards+dones out, moved over PCIe by the step kernel itself; obs/meta stay in HBM)",
             },
             "gpu_launches": gpu_launches,
             "roofline": {

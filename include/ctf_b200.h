@@ -207,9 +207,10 @@ int ctf_take_faults(ctf_handle_t h, void* stream, uint32_t* faults);
 
 /*
  * Host-buffer variant of ctf_step for callers that keep actions and rewards on
- * the host: copies actions_host (pinned or pageable, [B][N] uint8) to the
- * device, steps, copies rewards ([B][N] float32) and dones ([B] uint8) back and
- * waits for them.  Observations and metadata stay on the device in `out`.
+ * the host: actions_host ([B][N] uint8) in, rewards ([B][N] float32) and dones
+ * ([B] uint8) out, valid when the call returns.  Pinned (page-locked) buffers
+ * are accessed by the kernel directly over PCIe; pageable ones are staged with
+ * copies.  Observations and metadata stay on the device in `out`.
  */
 int ctf_step_host(ctf_handle_t h, ctf_state_t state, const uint8_t* actions_host, ctf_outputs_t out,
                   float* rewards_host, uint8_t* dones_host, void* stream);

@@ -331,6 +331,14 @@ def test_step_host_matches_device_step():
         host.step_host(a_h, r_h, d_h)
         assert torch.equal(dev.rewards.cpu(), r_h) and torch.equal(dev.dones.cpu(), d_h)
     assert torch.equal(dev.obs, host.obs)
+    # pageable host buffers take the staged-copy path and give the same results
+    pa, pr, pd = torch.empty((B, dev.N_AGENTS), dtype=torch.uint8), torch.empty((B, dev.N_AGENTS)), torch.empty((B,), dtype=torch.uint8)
+    for _ in range(5):
+        pa.copy_(torch.from_numpy(rng.integers(0, 9, (B, dev.N_AGENTS)).astype(np.uint8)))
+        dev.step(pa.cuda())
+        host.step_host(pa, pr, pd)
+        assert torch.equal(dev.rewards.cpu(), pr) and torch.equal(dev.dones.cpu(), pd)
+    assert torch.equal(dev.obs, host.obs)
 
 
 def test_outputs_written_into_caller_buffers():
