@@ -163,6 +163,35 @@ def test_constructor_keyword_variations(name, exp, overrides, kind):
     _run_against_oracle(exp, 96, steps, kind, seed=23, obs_every=15, stats="full", env_overrides=dict(overrides))
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_scenarios_and_configs(seed):
+    """The random maps / team layouts / HP tables pinned against the reference in test_oracle_vs_reference.py."""
+    from marl_ctf_development_b200 import GridworldCtfGPU
+    from random_scenarios import random_env_config
+
+    ec = random_env_config(seed)
+    B = 33
+    dtype = [torch.float32, torch.uint8, torch.bfloat16][seed % 3]
+    env = GridworldCtfGPU(**ec, num_envs=B, device="cuda:0", seed=77, env_id_base=seed, stats="full", obs_dtype=dtype)
+    orc = OracleBatch(env.ce, B, seed=77, env_id_base=seed)
+    pol = traces.make_policy("builder", env.ce)
+    rng = np.random.default_rng(seed)
+    u8 = dtype == torch.uint8
+    _assert_obs(env, orc, f"seed {seed} reset", u8)
+    for t in range(ec["GAME_STEPS"] + 2):
+        st = orc.state()
+        a = np.stack([pol(rng, st["pos"][b], st["has_flag"][b]) for b in range(B)])
+        _, _, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+        r_ref, d_ref = orc.step(a)
+        assert np.array_equal(bits(rew.cpu().numpy()), bits(r_ref)), f"seed {seed} t={t}: rewards differ"
+        assert np.array_equal(done.cpu().numpy(), d_ref)
+        if t % 10 == 0 or t >= ec["GAME_STEPS"] - 1:
+            _assert_batch_state(env, orc, f"seed {seed} t={t}")
+            _assert_obs(env, orc, f"seed {seed} t={t}", u8)
+    st, so = env.get_state(), orc.state()
+    assert np.array_equal(st["stats"], so["stats"]) and np.array_equal(st["visits"], so["visits"])
+
+
 def test_no_stats_variant_matches():
     _run_against_oracle("8_arena", 130, 80, "seek", seed=20, obs_every=20, stats="none")
 

@@ -135,3 +135,32 @@ def test_constructor_keyword_variations(name, exp, overrides, kind):
     assert np.array_equal(rs.agent_metrics(ref), st["stats"])
     vm = np.stack([ref.metrics["agent_visitation_maps"][i] for i in range(ce.N_AGENTS)])
     assert np.array_equal(vm, st["visits"])
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_scenarios_and_configs(seed):
+    """Random maps (grid 6..16, any FLIP_AXIS), team layouts, HP tables: reference == oracle step by step."""
+    from random_scenarios import random_env_config
+
+    ec = random_env_config(seed)
+    ce = compile_config(**ec)
+    ref = rs.make_injected_env(ec, seed=77, env_id=seed)
+    orc = OracleEnv(ce, seed=77, env_id=seed)
+    assert env_dims(ce) == ref.get_env_dims()
+    assert [int(t) for t in ce.TILES_USED] == [int(t) for t in ref.TILES_USED], "TILES_USED order (set iteration) differs"
+    pol = traces.make_policy("builder", ce)
+    rng = np.random.default_rng(seed)
+    for t in range(ec["GAME_STEPS"] + 2):
+        s = rs.snapshot(ref, ce.cfg.hp_scale)
+        a = pol(rng, s["pos"], s["has_flag"])
+        _, rr, rd = ref.step(a.tolist())
+        orr, od = orc.step(a)
+        assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"seed {seed} t={t}")
+        assert rd == od
+        assert np.array_equal(bits(np.array(rr, dtype=np.float32)), bits(orr)), (seed, t, rr, orr)
+        if t % 5 == 0:
+            ro, rm = rs.observations(ref)
+            oo, om = orc.observe()
+            assert np.array_equal(ro, oo), (seed, t)
+            assert np.array_equal(bits(rm), bits(om)), (seed, t, rm, om)
+    assert np.array_equal(rs.agent_metrics(ref), orc.state()["stats"])
