@@ -18,7 +18,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdio.h>
+#include <stdio.h>   // snprintf for error messages
 #include <string.h>
 
 #include <new>
