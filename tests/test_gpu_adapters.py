@@ -309,3 +309,30 @@ def test_bench_contract_keys():
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 2048 * 8
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_integration_md_ctypes_stub_runs_as_written():
+    """The reference-side binding shown in INTEGRATION.md §3 is executed verbatim (only the library path is made absolute)."""
+    import os
+    import re
+
+    from marl_ctf_development_b200 import _native
+
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = [b for b in blocks if b.startswith("import ctypes as C, torch")]
+    assert len(stub) == 1
+    code = stub[0].replace('C.CDLL("libctf_b200.so")', f'C.CDLL({_native.LIB_PATH!r})')
+    scope = {"env_config": experiment_env_config("8_arena")}
+    exec(compile(code, "INTEGRATION.md", "exec"), scope)
+    torch.cuda.synchronize()
+    obs, rew, envs = scope["obs"], scope["rew"], scope["envs"]
+    assert int(envs[:, 0].min()) == 1 and int(envs[:, 0].max()) == 1          # every env advanced one step
+    assert bool((obs[:, :, 0].sum((2, 3)) == 1).all()) and bool(torch.isfinite(rew).all())
+    # and it computed the same thing as the packaged binding
+    from marl_ctf_development_b200 import GridworldCtfGPU
+
+    env = GridworldCtfGPU(**experiment_env_config("8_arena"), num_envs=65536, device="cuda:0", seed=42)
+    env.step(scope["actions"])
+    assert torch.equal(env.obs, obs) and torch.equal(env.rewards, rew)
