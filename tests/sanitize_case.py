@@ -1,6 +1,6 @@
 """Small deterministic workload for compute-sanitizer (memcheck / racecheck / initcheck / synccheck).
 
-    python tools/sanitize_case.py && compute-sanitizer --tool racecheck python tools/sanitize_case.py
+    python tests/sanitize_case.py && compute-sanitizer --tool racecheck python tests/sanitize_case.py
 
 Covers reset, step (all obs dtypes, statistics + visitation maps), observe with explicit flags, stats_sum and
 the host-buffer step on three scenarios; checks the final state against the oracle so a silent corruption fails.
@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # traces.py
 
 import numpy as np
 import torch
