@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-EXPERIMENT = "8_arena"
+EXPERIMENT = "8_arena"  # BASELINE.json headline; --experiment selects another config for side measurements
 METRIC = "agent_steps_per_sec"
 UNIT = "agent-steps/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
@@ -121,6 +121,7 @@ def cpu_leg(envs_per_thread: int, steps: int, warm_steps: int = 20):
 
     threads = host_threads()
     ce = compile_config(**experiment_env_config(EXPERIMENT))
+    cpu_leg.dims = (ce.GRID_SIZE, ce.N_AGENTS, ce.n_channels)
     n_envs = envs_per_thread * threads
     batch = OracleBatch(ce, n_envs, seed=1)
     batch.run(warm_steps, 1, 1, threads)
@@ -143,8 +144,8 @@ def cpu_baseline_sample(n_agents: int, seconds: float = 8.0) -> dict:
         out[key + "_sample"] = f"{n_envs} envs x {steps} steps in {dt:.1f} s"
     return {
         "value": out["value"], "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": f"oracle/ctf_oracle.c (line-by-line port of gridworld_ctf.py) on {threads} threads, 8_arena, per step "
-                  f"obs+meta for all 8 agents then step(): {out['value_sample']}",
+        "sample": f"oracle/ctf_oracle.c (line-by-line port of gridworld_ctf.py) on {threads} threads, {EXPERIMENT}, per step "
+                  f"obs+meta for all agents then step(): {out['value_sample']}",
         "tuned_value": out["tuned_value"],
         "tuned_sample": f"same port with a scatter-style observation writer (not the reference's algorithm): {out['tuned_value_sample']}",
         "python_reference_note": "the unmodified Python reference measured 7.5e3 agent-steps/s per core (BASELINE.md §2); it cannot travel to this box",
@@ -162,7 +163,7 @@ def run_reference_arm(args) -> dict:
     dt = time.perf_counter() - t0
     value = n_envs * ce.N_AGENTS * args.steps / dt
     sample = (f"oracle/ctf_oracle.c (line-by-line port of gridworld_ctf.py; the Python reference cannot travel): {n_envs} envs "
-              f"({threads} threads x 256) x {args.steps} steps of 8_arena, obs+meta for all agents then step()")
+              f"({threads} threads x 256) x {args.steps} steps of {EXPERIMENT}, obs+meta for all agents then step()")
     return {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -176,14 +177,20 @@ def run_reference_arm(args) -> dict:
 
 
 def workload_config(envs_per_gpu: int, n_gpus: int) -> dict:
+    from marl_ctf_development_b200 import compile_config, experiment_env_config
+
+    ce = compile_config(**experiment_env_config(EXPERIMENT))
+    G, N, C = ce.GRID_SIZE, ce.N_AGENTS, ce.n_channels
+    out_mb = envs_per_gpu * N * (C * G * G + 6 + 2 * N) * 4 / 1e6
     return {
-        "workload": f"{EXPERIMENT} (scn.arena_iii, 15x15, 8 agents of 4 types), B={envs_per_gpu} envs/GPU, "
-                    "uniform random actions 0..8, float32 observations [B,8,14,15,15] + metadata [B,8,22]",
+        "workload": f"{EXPERIMENT} ({ce.SCENARIO_NAME}, {G}x{G}, {N} agents), B={envs_per_gpu} envs/GPU, "
+                    f"uniform random actions 0..8, float32 observations [B,{N},{C},{G},{G}] + metadata [B,{N},{6 + 2 * N}]",
         "envs_per_gpu": envs_per_gpu,
-        "n_agents": 8,
+        "n_agents": N,
         "obs_dtype": "float32",
         "parallelism": f"env-sharded x{n_gpus} (no collective in step; NCCL all-reduce of episode stats per episode)",
-        "l2": "per-step output (6.6 GB at B=65536) exceeds the 126 MB L2, no explicit flush",
+        "l2": f"per-step output is {out_mb:.0f} MB " + ("(exceeds the 126 MB L2, no explicit flush)" if out_mb > 126 else
+              "(fits the 126 MB L2: flushed between timed steps is NOT done, treat as L2-resident side measurement)"),
     }
 
 
@@ -322,11 +329,14 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-stats", action="store_true", help="skip the episode-statistics counters")
+    ap.add_argument("--experiment", default="8_arena", help="experiment config (side measurements; the headline is 8_arena)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--obs-dtype", choices=["float32", "uint8", "float16", "bfloat16"], default="float32",
                     help="float32 is the drop-in default and the headline; the narrower buffers are reported separately")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    global EXPERIMENT
+    EXPERIMENT = args.experiment
 
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -165,6 +165,14 @@ class GridworldCtfGPU:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _step_outputs(self):
+        """ctf_outputs_t of the bound buffers, rebuilt only when a buffer was rebound."""
+        key = (self.obs.data_ptr(), self.meta.data_ptr())
+        if getattr(self, "_out_key", None) != key:
+            self._out_key = key
+            self._out_struct = self._outputs()
+        return self._out_struct
+
     def _outputs(self, obs=True, meta=True, rewards=True, dones=True, obs_t=None, meta_t=None):
         o = self.obs if obs_t is None else obs_t
         m = self.meta if meta_t is None else meta_t
@@ -211,7 +219,9 @@ class GridworldCtfGPU:
     def step(self, actions):
         """actions: [B, N] integer tensor on the device (uint8 preferred). Returns (obs, meta, rewards, dones, action_mask)."""
         a = self._as_actions(actions)
-        _native.check(self._lib.ctf_step(self._handle, self._state_struct, C.c_void_p(a.data_ptr()), self._outputs(), self._stream()))
+        rc = self._lib.ctf_step(self._handle, self._state_struct, a.data_ptr(), self._step_outputs(), self._stream())
+        if rc:
+            _native.check(rc)
         self._last_actions = a  # keep alive until the launch has consumed it
         if self.validate_actions:
             self.raise_on_faults()
@@ -246,6 +256,9 @@ class GridworldCtfGPU:
         return obs_t, meta_t
 
     def _as_actions(self, actions) -> torch.Tensor:
+        if (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device
+                and actions.is_contiguous() and tuple(actions.shape) == (self.num_envs, self.N_AGENTS)):
+            return actions  # the common case: no conversion, no copy
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions))
         if tuple(actions.shape) != (self.num_envs, self.N_AGENTS):
