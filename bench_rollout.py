@@ -34,6 +34,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--policy-dtype", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--chunk", type=int, default=32768, help="policy samples per forward")
+    ap.add_argument("--channels-last", action="store_true", help="run the convolutions in NHWC (stock torch option)")
+    ap.add_argument("--obs-dtype", choices=["float32", "bfloat16"], default=None,
+                    help="env observation buffer type (default: bfloat16 when the policy runs in bf16)")
     args = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -43,11 +46,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = args.envs
+    obs_dtype = args.obs_dtype or ("bfloat16" if args.policy_dtype == "bf16" else "float32")
+    torch.backends.cudnn.benchmark = True
     env = GridworldCtfGPU(**experiment_env_config("8_arena"), num_envs=B, device=dev, seed=0, env_id_base=rank * B,
-                          reverse_team1_actions=True, stats="counters")
+                          reverse_team1_actions=True, stats="counters", obs_dtype=getattr(torch, obs_dtype))
     N, C, G, M = env.N_AGENTS, env.n_channels, env.GRID_SIZE, env.meta_size
     torch.manual_seed(rank)
     pols = [CtfPolicy(9, C, G, M).to(dev).eval() for _ in range(2)]
+    if args.channels_last:
+        pols = [p.to(memory_format=torch.channels_last) for p in pols]
     teams = [torch.tensor([i for i in range(N) if env.AGENT_TEAMS[i] == t], device=dev) for t in (0, 1)]
     actions = torch.empty((B, N), dtype=torch.uint8, device=dev)
     amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.policy_dtype == "bf16")
@@ -57,6 +64,8 @@ def main():
         for idx, pol in zip(teams, pols):
             k = idx.numel()
             g = obs[:, idx].reshape(B * k, C, G, G)
+            if args.channels_last:
+                g = g.contiguous(memory_format=torch.channels_last)
             m = meta[:, idx].reshape(B * k, M)
             f = env.use_action_mask[idx].unsqueeze(0).expand(B, k).reshape(B * k)
             outs = []
@@ -98,7 +107,8 @@ def main():
             "env_only_value": total / (ms_env * 1e-3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_full / args.steps, "env_ms_per_step": ms_env / args.steps,
             "config": {"workload": f"8_arena self-play rollout, B={B} envs/GPU, CtfPolicy (agent_network.py architecture) "
-                                   f"for both teams, policy dtype {args.policy_dtype}, float32 observations", "envs_per_gpu": B},
+                                   f"for both teams, policy dtype {args.policy_dtype}, {obs_dtype} observations"
+                                   f"{', channels_last' if args.channels_last else ''}", "envs_per_gpu": B},
             "data": "synthetic (random-init policies)",
         }), flush=True)
     if world > 1:
