@@ -242,6 +242,9 @@ def run_ours(args) -> dict | None:
     for _ in range(W):
         one_step(step_idx)
         step_idx += 1
+    graph = None
+    if args.graph_steps > 0:
+        graph = env.make_step_graph(actions[0], steps_per_replay=args.graph_steps)
     # ---- timed region: K steps, CUDA events on the launching stream, barrier + synchronize on both sides
     barrier()
     sampler = ClockSampler(local_rank)
@@ -249,9 +252,15 @@ def run_ours(args) -> dict | None:
     launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
-        one_step(step_idx)
-        step_idx += 1
+    if graph is None:
+        for _ in range(K):
+            one_step(step_idx)
+            step_idx += 1
+    else:
+        for _ in range(K // args.graph_steps):
+            graph.replay()
+        launches = (K // args.graph_steps) * args.graph_steps
+        K = launches
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -329,6 +338,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-stats", action="store_true", help="skip the episode-statistics counters")
+    ap.add_argument("--graph-steps", type=int, default=0,
+                    help="side measurement: replay a CUDA graph of this many captured steps (launch-bound small batches)")
     ap.add_argument("--experiment", default="8_arena", help="experiment config (side measurements; the headline is 8_arena)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--obs-dtype", choices=["float32", "uint8", "float16", "bfloat16"], default="float32",

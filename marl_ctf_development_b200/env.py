@@ -227,6 +227,28 @@ class GridworldCtfGPU:
             self.raise_on_faults()
         return self.obs, self.meta, self.rewards, self.dones, self.action_mask
 
+    def make_step_graph(self, actions: torch.Tensor, steps_per_replay: int = 1):
+        """Captures ``steps_per_replay`` step launches on static buffers into a CUDA graph (launch-bound small batches).
+
+        ``actions`` is the static uint8 [B, N] device tensor the caller refills before each replay (with
+        steps_per_replay > 1 the same actions are applied every step — useful for no-op/benchmark loops only).
+        Returns the ``torch.cuda.CUDAGraph``; call ``.replay()``.  ctf_step makes no allocation and no host
+        synchronisation, so it is capturable as is; a policy forward can be captured in the same graph by the caller.
+        """
+        a = self._as_actions(actions)
+        if a.data_ptr() != actions.data_ptr():
+            raise ValueError("actions must already be a contiguous uint8 [B, N] tensor on the env's device")
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.step(a)  # warm-up outside capture
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(int(steps_per_replay)):
+                self.step(a)
+        return graph
+
     def step_host(self, actions_host: torch.Tensor, rewards_host: torch.Tensor, dones_host: torch.Tensor):
         """Host-buffer step: uint8 actions [B,N] (pinned) in, float32 rewards [B,N] / uint8 dones [B] out; obs/meta stay on the device."""
         B, N = self.num_envs, self.N_AGENTS

@@ -401,3 +401,26 @@ def test_half_rounding_on_device_matches_numpy():
         assert m[0, 0] == np.float32(np.float16(step / 500))
         assert m[0, 1] == np.float32(np.float16((c0 + 1) / (c1 + 1)))
         assert m[1, 1] == np.float32(np.float16((c1 + 1) / (c0 + 1)))
+
+
+def test_step_is_cuda_graph_capturable():
+    """A captured step replays bit-identically to eager steps (one warm-up step is taken by make_step_graph)."""
+    B = 512
+    eager = _env("0_the_split", B, seed=8, stats="counters")
+    graphed = _env("0_the_split", B, seed=8, stats="counters")
+    acts = torch.zeros((B, eager.N_AGENTS), dtype=torch.uint8, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    acts.copy_(torch.randint(0, 9, acts.shape, dtype=torch.uint8, device="cuda", generator=gen))
+    eager.step(acts)
+    graph = graphed.make_step_graph(acts)       # takes the same first step as its warm-up
+    eager.step(acts)                            # the capture itself does not execute: replay it once to stay aligned
+    graph.replay()
+    for _ in range(50):
+        acts.copy_(torch.randint(0, 9, acts.shape, dtype=torch.uint8, device="cuda", generator=gen))
+        eager.step(acts)
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(eager.obs, graphed.obs) and torch.equal(eager.rewards, graphed.rewards)
+    se, sg = eager.get_state(), graphed.get_state()
+    for k in STATE_KEYS + ("step", "stats"):
+        assert np.array_equal(se[k], sg[k]), k
