@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CTF_ABI_VERSION 1
+#define CTF_ABI_VERSION 2
 
 #define CTF_MAX_AGENTS 8    /* largest AGENT_STARTING_POSITIONS in scenarios.py has 8 entries */
 #define CTF_MAX_GRID 16     /* GRID_SIZE <= 16 (shipped maps: 11, 13, 15) */
@@ -137,6 +137,9 @@ typedef struct ctf_state {
 /* Device output buffers of one reset()/step(). Any pointer may be NULL to skip that output. */
 typedef struct ctf_outputs {
     void* obs;        /* [B][N][C][G][G] float32 (or uint8 / float16 / bfloat16): standardise_state(i, obs_reverse[i]) for every agent */
+    uint32_t* obs_bits; /* [B][N][bits_words_per_agent] packed copy of the same observations, 1 bit per element:
+                         element c*G*G + p of agent a is bit (c*G*G + p) % 32 of word a*wpa + (c*G*G + p) / 32.
+                         For rollout storage (32x smaller than float32); ctf_unpack_obs expands it. */
     float* meta;      /* [B][N][6+2N] float32: get_env_metadata(i) (fp16-rounded values) */
     float* rewards;   /* [B][N] float32 */
     uint8_t* dones;   /* [B] 0/1 */
@@ -147,6 +150,8 @@ typedef struct ctf_sizes {
     size_t grid_bytes, agents_bytes, envs_bytes, stats_bytes, visits_bytes;
     size_t obs_bytes, meta_bytes, rewards_bytes, dones_bytes;
     size_t obs_elems_per_env, meta_elems_per_env;
+    size_t obs_bits_bytes;       /* bytes of outputs.obs_bits */
+    size_t bits_words_per_agent; /* ceil(C*G*G / 32) */
 } ctf_sizes_t;
 
 typedef struct ctf_env* ctf_handle_t;
@@ -194,6 +199,13 @@ int ctf_step(ctf_handle_t h, ctf_state_t state, const uint8_t* actions, ctf_outp
  * reverse_flags: host uint8 [N] (NULL = cfg.obs_reverse).
  */
 int ctf_observe(ctf_handle_t h, ctf_state_t state, const uint8_t* reverse_flags, ctf_outputs_t out, void* stream);
+
+/*
+ * Expands packed observations (outputs.obs_bits layout, any number of agent blocks, e.g. a minibatch gathered
+ * from a rollout buffer) into out[n_agent_blocks][C][G][G] of ctf_obs_dtype out_dtype — what the policy
+ * consumes at PPO update time (ppo.py:298, 440) without ever holding the float32 rollout in memory.
+ */
+int ctf_unpack_obs(ctf_handle_t h, const uint32_t* packed, void* out, int out_dtype, int64_t n_agent_blocks, void* stream);
 
 /*
  * Sum of the per-env counters over this handle's envs: device int64

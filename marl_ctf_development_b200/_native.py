@@ -21,11 +21,12 @@ EXPORTS = (
     "ctf_reset",
     "ctf_step",
     "ctf_observe",
+    "ctf_unpack_obs",
     "ctf_stats_sum",
     "ctf_take_faults",
     "ctf_step_host",
 )
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CtfState(C.Structure):
@@ -39,7 +40,7 @@ class CtfState(C.Structure):
 
 
 class CtfOutputs(C.Structure):
-    _fields_ = [("obs", C.c_void_p), ("meta", C.c_void_p), ("rewards", C.c_void_p), ("dones", C.c_void_p)]
+    _fields_ = [("obs", C.c_void_p), ("obs_bits", C.c_void_p), ("meta", C.c_void_p), ("rewards", C.c_void_p), ("dones", C.c_void_p)]
 
 
 class CtfSizes(C.Structure):
@@ -58,6 +59,8 @@ class CtfSizes(C.Structure):
             "dones_bytes",
             "obs_elems_per_env",
             "meta_elems_per_env",
+            "obs_bits_bytes",
+            "bits_words_per_agent",
         )
     ]
 
@@ -101,6 +104,7 @@ def load():
     L.ctf_reset.argtypes = [C.c_void_p, CtfState, CtfOutputs, C.c_int, C.c_void_p]
     L.ctf_step.argtypes = [C.c_void_p, CtfState, C.c_void_p, CtfOutputs, C.c_void_p]
     L.ctf_observe.argtypes = [C.c_void_p, CtfState, C.c_void_p, CtfOutputs, C.c_void_p]
+    L.ctf_unpack_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
     L.ctf_stats_sum.argtypes = [C.c_void_p, CtfState, C.c_void_p, C.c_void_p]
     L.ctf_take_faults.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     L.ctf_step_host.argtypes = [C.c_void_p, CtfState, C.c_void_p, CtfOutputs, C.c_void_p, C.c_void_p, C.c_void_p]

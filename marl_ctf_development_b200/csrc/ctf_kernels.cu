@@ -49,6 +49,7 @@ struct DevPlan {
     double reward_step, reward_capture, reward_tag, capture_punish, win_margin, loss_margin;
     int G, N, C, GG, M, E;        // E = N*C*G*G observation elements per env
     int bits_words;               // words of the per-env observation bit string (incl. 1 pad word)
+    int wpa;                      // words per agent of the packed observation output: ceil(C*G*G / 32)
     int game_steps, flip_axis;
     int use_adjusted_rewards, home_flag_capture, drop_flag_when_no_hp, reverse_team1_actions;
     int heal_q, vault_cost_q, vault_min_q;
@@ -74,6 +75,7 @@ struct Launch {
     uint8_t* visits;
     // outputs
     void* obs;
+    uint32_t* obs_bits;
     float* meta;
     float* rewards;
     uint8_t* dones;
@@ -203,12 +205,10 @@ __device__ __forceinline__ void store_vec(uint4* p, uint4 v) {
 #endif
 }
 
-template <typename T>
-__device__ __forceinline__ void write_obs(const DevPlan& P, const WarpMem& w, uint32_t me, uint32_t rev_mask,
-                                          T* __restrict__ obs_env, int lane) {
-    constexpr int VEC = 16 / (int)sizeof(T);
+// Builds the env's observation block as one bit per element in shared memory (w.bits): element
+// e = (a*C + c)*G*G + p of the [N][C][G][G] block is bit e.
+__device__ __forceinline__ void build_obs_bits(const DevPlan& P, const WarpMem& w, uint32_t me, uint32_t rev_mask, int lane) {
     const int N = P.N, GG = P.GG, CGG = P.C * P.GG;
-
     // 1. clear the bit string
     {
         uint4* b4 = reinterpret_cast<uint4*>(w.bits);
@@ -254,22 +254,27 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const WarpMem& w, ui
         }
     }
     __syncwarp();
-    // 4. stream: element e of the env's [N][C][G][G] block is bit e
-    const int E = P.E;
-    const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(obs_env) / sizeof(T)) % VEC);
-    const int head = mis ? min(VEC - (int)mis, E) : 0;
-    const int nvec = (E - head) / VEC;
-    const int tail = E - head - nvec * VEC;
-    if (lane < head) obs_env[lane] = from_bit<T>((w.bits[lane >> 5] >> (lane & 31)) & 1u);
+}
+
+// Streams `nbits` elements (bit e of `bits` -> element e) to `out` with 128-bit stores; `bits` needs one readable
+// word past the last one.  Handles any alignment of `out` (scalar head/tail, funnel-shifted body).
+template <typename T>
+__device__ __forceinline__ void stream_bits(const uint32_t* bits, int nbits, T* __restrict__ out, int lane) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(out) / sizeof(T)) % VEC);
+    const int head = mis ? min(VEC - (int)mis, nbits) : 0;
+    const int nvec = (nbits - head) / VEC;
+    const int tail = nbits - head - nvec * VEC;
+    if (lane < head) out[lane] = from_bit<T>((bits[lane >> 5] >> (lane & 31)) & 1u);
     if (lane < tail) {
         const int e = head + nvec * VEC + lane;
-        obs_env[e] = from_bit<T>((w.bits[e >> 5] >> (e & 31)) & 1u);
+        out[e] = from_bit<T>((bits[e >> 5] >> (e & 31)) & 1u);
     }
-    uint4* __restrict__ vp = reinterpret_cast<uint4*>(obs_env + head);
-    if ((head & (VEC - 1)) == 0 && sizeof(T) == 4) {
+    uint4* __restrict__ vp = reinterpret_cast<uint4*>(out + head);
+    if (head == 0 && sizeof(T) == 4) {
         // aligned float path: vector i is nibble (i & 7) of word (i >> 3)
         const int sh = (lane & 7) * 4;
-        const uint32_t* wp = w.bits + (lane >> 3);
+        const uint32_t* wp = bits + (lane >> 3);
         int i = lane;
 #pragma unroll 4
         for (; i < nvec; i += 32, wp += 4) {
@@ -279,10 +284,33 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const WarpMem& w, ui
 #pragma unroll 2
         for (int i = lane; i < nvec; i += 32) {
             const int o = head + i * VEC;
-            const uint32_t lo = w.bits[o >> 5], hi = w.bits[(o >> 5) + 1];
+            const uint32_t lo = bits[o >> 5], hi = bits[(o >> 5) + 1];
             store_vec(vp + i, expand_bits<T>(__funnelshift_r(lo, hi, o & 31)));
         }
     }
+}
+
+// Packed copy of the observation block for rollout storage: agent a's C*G*G bits start at word a*wpa
+// (32x smaller than float32; ctf_unpack_obs expands it again).
+__device__ __forceinline__ void store_packed(const DevPlan& P, const WarpMem& w, uint32_t* __restrict__ out_env, int lane) {
+    const int CGG = P.C * P.GG, wpa = P.wpa, total = P.N * wpa;
+    for (int i = lane; i < total; i += 32) {
+        const int a = i / wpa, j = i - a * wpa;
+        const int o = a * CGG + 32 * j;
+        uint32_t v = __funnelshift_r(w.bits[o >> 5], w.bits[(o >> 5) + 1], o & 31);
+        const int valid = CGG - 32 * j;            // bits of this word that belong to agent a
+        if (valid < 32) v &= (1u << valid) - 1u;
+        out_env[i] = v;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void write_obs(const DevPlan& P, const Launch& L, const WarpMem& w, long long env, uint32_t me,
+                                          uint32_t rev_mask, int lane) {
+    if (!L.obs && !L.obs_bits) return;
+    build_obs_bits(P, w, me, rev_mask, lane);
+    if (L.obs_bits) store_packed(P, w, L.obs_bits + env * (long long)(P.N * P.wpa), lane);
+    if (L.obs) stream_bits<T>(w.bits, P.E, reinterpret_cast<T*>(L.obs) + env * (long long)P.E, lane);
 }
 
 __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int step, int caps0, int caps1,
@@ -378,7 +406,7 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ DevP
     const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
                                                         : __ballot_sync(kFull, lane < P.N && P.obs_rev[li]);
     if (L.meta) write_meta(P, me, 0, 0, 0, L.meta + env * (long long)P.N * P.M, lane);
-    if (L.obs) write_obs<T>(P, w, me, rev_mask, reinterpret_cast<T*>(L.obs) + env * (long long)P.E, lane);
+    write_obs<T>(P, L, w, env, me, rev_mask, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) k_observe(const __grid_constant__ De
     const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
                                                         : __ballot_sync(kFull, lane < P.N && P.obs_rev[li]);
     if (L.meta) write_meta(P, me, (int)ev.x, (int)ev.z, (int)ev.w, L.meta + env * (long long)P.N * P.M, lane);
-    if (L.obs) write_obs<T>(P, w, me, rev_mask, reinterpret_cast<T*>(L.obs) + env * (long long)P.E, lane);
+    write_obs<T>(P, L, w, env, me, rev_mask, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -650,7 +678,24 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
     const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
                                                         : __ballot_sync(kFull, lane < N && P.obs_rev[li]);
     if (L.meta) write_meta(P, me, step, caps0, caps1, L.meta + env * (long long)N * P.M, lane);
-    if (L.obs) write_obs<T>(P, w, me, rev_mask, reinterpret_cast<T*>(L.obs) + env * (long long)P.E, lane);
+    write_obs<T>(P, L, w, env, me, rev_mask, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed observations -> policy input: one warp per agent block (wpa words -> C*G*G elements)
+// ------------------------------------------------------------------------------------------------
+constexpr int kUnpackWarps = 8;
+template <typename T>
+__global__ void __launch_bounds__(kUnpackWarps * 32) k_unpack(const uint32_t* __restrict__ packed, T* __restrict__ out,
+                                                             long long n_blocks, int nbits, int wpa) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long blk = (long long)blockIdx.x * kUnpackWarps + warp;
+    if (blk >= n_blocks) return;
+    uint32_t* bits = reinterpret_cast<uint32_t*>(smem_raw) + warp * (wpa + 4);
+    for (int i = lane; i < wpa + 1; i += 32) bits[i] = i < wpa ? __ldg(packed + blk * wpa + i) : 0u;
+    __syncwarp();
+    stream_bits<T>(bits, nbits, out + blk * (long long)nbits, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -720,6 +765,7 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
     P.capture_punish = c.capture_punish; P.win_margin = c.win_margin_scalar; P.loss_margin = c.loss_margin_scalar;
     P.G = G; P.N = N; P.C = c.n_channels; P.GG = G * G; P.M = 6 + 2 * N; P.E = N * c.n_channels * G * G;
     P.bits_words = (P.E + 31) / 32 + 1;
+    P.wpa = (c.n_channels * G * G + 31) / 32;
     P.game_steps = c.game_steps; P.flip_axis = c.flip_axis;
     P.use_adjusted_rewards = c.use_adjusted_rewards; P.home_flag_capture = c.home_flag_capture;
     P.drop_flag_when_no_hp = c.drop_flag_when_no_hp; P.reverse_team1_actions = c.reverse_team1_actions;
@@ -858,6 +904,8 @@ extern "C" int ctf_get_sizes(ctf_handle_t h, ctf_sizes_t* s) {
     s->stats_bytes = h->stats_level > 0 ? B * CTF_N_METRICS * P.N * 4 : 0;
     s->visits_bytes = h->stats_level > 1 ? B * P.N * P.GG : 0;
     s->obs_bytes = B * P.E * elem;
+    s->obs_bits_bytes = B * P.N * P.wpa * 4;
+    s->bits_words_per_agent = (size_t)P.wpa;
     s->meta_bytes = B * P.N * P.M * 4;
     s->rewards_bytes = B * P.N * 4;
     s->dones_bytes = B;
@@ -877,7 +925,7 @@ static int make_launch(ctf_handle_t h, const ctf_state_t& st, const ctf_outputs_
     L.grid = st.grid; L.agents = reinterpret_cast<unsigned long long*>(st.agents); L.envs = reinterpret_cast<uint4*>(st.envs);
     L.stats = h->stats_level > 0 ? st.stats : nullptr;
     L.visits = h->stats_level > 1 ? st.visits : nullptr;
-    L.obs = out.obs; L.meta = out.meta; L.rewards = out.rewards; L.dones = out.dones;
+    L.obs = out.obs; L.obs_bits = out.obs_bits; L.meta = out.meta; L.rewards = out.rewards; L.dones = out.dones;
     L.faults = h->faults;
     L.B = h->B;
     L.seed_lo = (uint32_t)(h->seed & 0xFFFFFFFFu); L.seed_hi = (uint32_t)(h->seed >> 32);
@@ -952,6 +1000,25 @@ extern "C" int ctf_observe(ctf_handle_t h, ctf_state_t st, const uint8_t* revers
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     with_obs_type(h->obs_dtype, [&](auto tag) {
         k_observe<decltype(tag)><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+    });
+    CTF_CUDA(cudaGetLastError());
+    return CTF_OK;
+}
+
+extern "C" int ctf_unpack_obs(ctf_handle_t h, const uint32_t* packed, void* out, int out_dtype, int64_t n_agent_blocks,
+                              void* stream) {
+    if (!h || !packed || !out) return fail(CTF_ERR_INVALID, "null argument");
+    if (out_dtype < CTF_OBS_F32 || out_dtype > CTF_OBS_BF16) return fail(CTF_ERR_INVALID, "unknown obs dtype");
+    if (n_agent_blocks < 0) return fail(CTF_ERR_INVALID, "negative block count");
+    if (n_agent_blocks == 0) return CTF_OK;
+    CTF_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int nbits = h->plan.C * h->plan.GG, wpa = h->plan.wpa;
+    const unsigned grid = (unsigned)((n_agent_blocks + kUnpackWarps - 1) / kUnpackWarps);
+    const size_t smem = (size_t)kUnpackWarps * (wpa + 4) * sizeof(uint32_t);
+    with_obs_type(out_dtype, [&](auto tag) {
+        using T = decltype(tag);
+        k_unpack<T><<<grid, kUnpackWarps * 32, smem, s>>>(packed, static_cast<T*>(out), n_agent_blocks, nbits, wpa);
     });
     CTF_CUDA(cudaGetLastError());
     return CTF_OK;

@@ -64,6 +64,8 @@ class GridworldCtfGPU:
         validate_actions=False,
         obs_out=None,
         meta_out=None,
+        packed_obs=False,
+        dense_obs=True,
     ):
         self._handle = None
         self._lib = _native.load()  # raises when the extension is missing
@@ -130,9 +132,17 @@ class GridworldCtfGPU:
         self._stats = torch.zeros((B, N_METRICS, N), dtype=torch.int32, device=dev) if self.stats_level > 0 else None
         self._visits = torch.zeros((B, N, G, G), dtype=torch.uint8, device=dev) if self.stats_level > 1 else None
         # ---- outputs (the policy's input buffers unless the caller binds its own)
-        self.obs = torch.empty((B, N, Cn, G, G), dtype=obs_dtype, device=dev) if obs_out is None else obs_out
+        # dense_obs=False skips the [B,N,C,G,G] buffer (storage-only use: packed_obs=True + unpack_obs on demand)
+        self.obs = None
+        if dense_obs:
+            self.obs = torch.empty((B, N, Cn, G, G), dtype=obs_dtype, device=dev) if obs_out is None else obs_out
+            self._check_out(self.obs, (B, N, Cn, G, G), obs_dtype, "obs_out")
+        elif not packed_obs:
+            raise ValueError("dense_obs=False needs packed_obs=True")
+        # packed copy of the same observations, 1 bit per element, [B, N, ceil(C*G*G/32)] int32 (rollout storage)
+        self.bits_words_per_agent = int(sizes.bits_words_per_agent)
+        self.obs_bits = torch.zeros((B, N, self.bits_words_per_agent), dtype=torch.int32, device=dev) if packed_obs else None
         self.meta = torch.empty((B, N, M), dtype=torch.float32, device=dev) if meta_out is None else meta_out
-        self._check_out(self.obs, (B, N, Cn, G, G), obs_dtype, "obs_out")
         self._check_out(self.meta, (B, N, M), torch.float32, "meta_out")
         self.rewards = torch.zeros((B, N), dtype=torch.float32, device=dev)
         self.dones = torch.zeros((B,), dtype=torch.uint8, device=dev)
@@ -154,8 +164,9 @@ class GridworldCtfGPU:
             flags = [0] * N
             if N > 1:
                 flags[1] = 1
-            obs, _ = self.observe(reverse_flags=flags, into_new=True)
-            assert N < 2 or bool(torch.equal(obs[0, 0], obs[0, 1])), "map symmetry check failed (gridworld_ctf.py:477)"
+            if self.obs is not None:
+                obs, _ = self.observe(reverse_flags=flags, into_new=True)
+                assert N < 2 or bool(torch.equal(obs[0, 0], obs[0, 1])), "map symmetry check failed (gridworld_ctf.py:477)"
 
     # ------------------------------------------------------------------ plumbing
     def _check_out(self, t, shape, dtype, name):
@@ -167,17 +178,19 @@ class GridworldCtfGPU:
 
     def _step_outputs(self):
         """ctf_outputs_t of the bound buffers, rebuilt only when a buffer was rebound."""
-        key = (self.obs.data_ptr(), self.meta.data_ptr())
+        key = (self.obs.data_ptr() if self.obs is not None else 0, self.meta.data_ptr())
         if getattr(self, "_out_key", None) != key:
             self._out_key = key
             self._out_struct = self._outputs()
         return self._out_struct
 
-    def _outputs(self, obs=True, meta=True, rewards=True, dones=True, obs_t=None, meta_t=None):
+    def _outputs(self, obs=True, meta=True, rewards=True, dones=True, obs_t=None, meta_t=None, bits=True):
         o = self.obs if obs_t is None else obs_t
         m = self.meta if meta_t is None else meta_t
         return _native.CtfOutputs(
-            o.data_ptr() if obs else None, m.data_ptr() if meta else None,
+            o.data_ptr() if (obs and o is not None) else None,
+            self.obs_bits.data_ptr() if (bits and self.obs_bits is not None) else None,
+            m.data_ptr() if meta else None,
             self.rewards.data_ptr() if rewards else None, self.dones.data_ptr() if dones else None,
         )
 
@@ -268,14 +281,36 @@ class GridworldCtfGPU:
 
     def observe(self, reverse_flags=None, into_new=False):
         """standardise_state / get_env_metadata of the current state for all agents; reverse_flags: per-agent reverse_grid."""
+        if self.obs is None:
+            raise RuntimeError("this env was created with dense_obs=False; use obs_bits / unpack_obs")
         obs_t = torch.empty_like(self.obs) if into_new else self.obs
         meta_t = torch.empty_like(self.meta) if into_new else self.meta
         rf = None
         if reverse_flags is not None:
             rf = (C.c_uint8 * self.N_AGENTS)(*[int(bool(x)) for x in reverse_flags])
-        out = self._outputs(rewards=False, dones=False, obs_t=obs_t, meta_t=meta_t)
+        out = self._outputs(rewards=False, dones=False, obs_t=obs_t, meta_t=meta_t, bits=False)
         _native.check(self._lib.ctf_observe(self._handle, self._state_struct, rf, out, self._stream()))
         return obs_t, meta_t
+
+    def unpack_obs(self, packed: torch.Tensor, dtype=torch.float32, out=None) -> torch.Tensor:
+        """Expands packed observations [..., words_per_agent] int32 (any leading shape, e.g. a minibatch gathered from
+        a rollout buffer of ``env.obs_bits`` snapshots) into [..., C, G, G] of ``dtype`` with the CUDA unpack kernel."""
+        if dtype not in _OBS_DTYPES:
+            raise ValueError("dtype must be torch.float32, torch.uint8, torch.float16 or torch.bfloat16")
+        wpa, Cn, G = self.bits_words_per_agent, self.n_channels, self.GRID_SIZE
+        if packed.dtype != torch.int32 or packed.shape[-1] != wpa or packed.device != self.device:
+            raise ValueError(f"packed must be an int32 tensor [..., {wpa}] on {self.device}")
+        packed = packed.contiguous()
+        lead = tuple(packed.shape[:-1])
+        n = int(packed.numel() // wpa)
+        if out is None:
+            out = torch.empty(lead + (Cn, G, G), dtype=dtype, device=self.device)
+        elif tuple(out.shape) != lead + (Cn, G, G) or out.dtype != dtype or not out.is_contiguous() or out.device != self.device:
+            raise ValueError("out has the wrong shape / dtype / layout")
+        _native.check(
+            self._lib.ctf_unpack_obs(self._handle, packed.data_ptr(), out.data_ptr(), _OBS_DTYPES[dtype], n, self._stream())
+        )
+        return out
 
     def _as_actions(self, actions) -> torch.Tensor:
         if (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device

@@ -23,7 +23,7 @@ import torch
 class Rollout:
     """Layout of ppo.py:298-305 with the env axis batched: index [step * apt + agent_offset, env]."""
 
-    grid_states: torch.Tensor      # [T*apt, B, C, G, G]
+    grid_states: torch.Tensor      # [T*apt, B, C, G, G]  (or packed: [T*apt, B, words_per_agent] int32, see unpack_grid_states)
     metadata_states: torch.Tensor  # [T*apt, B, M]
     actions: torch.Tensor          # [T*apt, B]
     use_action_mask: torch.Tensor  # [T*apt, B]
@@ -34,6 +34,13 @@ class Rollout:
     next_grid_state: torch.Tensor  # [B, C, G, G]
     next_metadata_state: torch.Tensor  # [B, M]
     next_done: torch.Tensor        # [B]
+    packed: bool = False
+
+    def unpack_grid_states(self, env, index=slice(None), dtype=torch.float32) -> torch.Tensor:
+        """grid_states[index] as [..., C, G, G] of ``dtype`` — expands packed storage with the CUDA unpack kernel
+        (the PPO update gathers minibatches this way, ppo.py:440-449, without a float32 rollout buffer)."""
+        g = self.grid_states[index]
+        return env.unpack_obs(g, dtype=dtype) if self.packed else g.to(dtype)
 
 
 def _require_folded_reversal(env):
@@ -50,7 +57,8 @@ def collect_rollout(env, agent, opponent, train_team1=True, num_env_steps=None, 
     """One rollout of every env (ppo.py:31-131).  ``train_team1=True`` trains team 0 (ppo.py:274-279).
 
     num_env_steps defaults to GAME_STEPS (one episode per rollout, as num_steps == GAME_STEPS in every
-    experiment).  obs_storage_dtype=torch.uint8 stores the {0,1} observations packed 4x smaller.
+    experiment).  obs_storage_dtype=torch.uint8 stores the {0,1} observations 4x smaller; obs_storage_dtype="packed"
+    stores the kernel's 1-bit-per-element copy (env created with packed_obs=True), 32x smaller than float32.
     """
     _require_folded_reversal(env)
     team = 0 if train_team1 else 1
@@ -63,8 +71,12 @@ def collect_rollout(env, agent, opponent, train_team1=True, num_env_steps=None, 
     theirs_t = torch.tensor(theirs, device=dev)
     mask_flags = env.use_action_mask  # [N] float, AGENT_TYPE_ACTION_MASK per agent
 
+    packed = obs_storage_dtype == "packed"
+    if packed and env.obs_bits is None:
+        raise ValueError('obs_storage_dtype="packed" needs an env created with packed_obs=True')
     out = Rollout(
-        grid_states=torch.zeros((T * apt, B, C, G, G), dtype=obs_storage_dtype, device=dev),
+        grid_states=(torch.zeros((T * apt, B, env.bits_words_per_agent), dtype=torch.int32, device=dev) if packed
+                     else torch.zeros((T * apt, B, C, G, G), dtype=obs_storage_dtype, device=dev)),
         metadata_states=torch.zeros((T * apt, B, M), device=dev),
         actions=torch.zeros((T * apt, B), device=dev),
         use_action_mask=torch.zeros((T * apt, B), device=dev),
@@ -72,7 +84,7 @@ def collect_rollout(env, agent, opponent, train_team1=True, num_env_steps=None, 
         rewards=torch.zeros((T * apt, B), device=dev),
         dones=torch.zeros((T * apt, B), device=dev),
         values=torch.zeros((T * apt, B), device=dev),
-        next_grid_state=torch.empty(0), next_metadata_state=torch.empty(0), next_done=torch.empty(0),
+        next_grid_state=torch.empty(0), next_metadata_state=torch.empty(0), next_done=torch.empty(0), packed=packed,
     )
     obs, meta, _ = env.reset()                                                    # ppo.py:57
     actions = torch.empty((B, N), dtype=torch.uint8, device=dev)
@@ -85,7 +97,10 @@ def collect_rollout(env, agent, opponent, train_team1=True, num_env_steps=None, 
         a, logp, _, v = agent.get_action_and_value(
             g.reshape(apt * B, C, G, G).float(), m.reshape(apt * B, M), flags.reshape(apt * B)
         )
-        out.grid_states[sl] = g.to(obs_storage_dtype)
+        if packed:
+            out.grid_states[sl] = env.obs_bits[:, mine_t].transpose(0, 1)
+        else:
+            out.grid_states[sl] = g.to(obs_storage_dtype)
         out.metadata_states[sl] = m
         out.values[sl] = v.reshape(apt, B)
         out.actions[sl] = a.reshape(apt, B).float()

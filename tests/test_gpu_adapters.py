@@ -90,6 +90,27 @@ def test_batched_rollout_matches_reference_loop(train_team1):
     assert tuple(ro.grid_states.shape) == (T * apt, B, env.n_channels, env.GRID_SIZE, env.GRID_SIZE)
 
 
+def test_rollout_with_packed_observation_storage():
+    """Packed rollout storage (1 bit per element) unpacks to exactly the float32 rollout."""
+    from marl_ctf_development_b200 import GridworldCtfGPU
+    from marl_ctf_development_b200.rollout import collect_rollout
+
+    ec = experiment_env_config("8_arena")
+    B, T = 24, 40
+    n_obs, n_meta = 14 * 15 * 15, 22
+    agent, opponent = HashPolicy(n_obs, n_meta, 1).cuda(), HashPolicy(n_obs, n_meta, 2).cuda()
+    env_a = GridworldCtfGPU(**ec, num_envs=B, device="cuda:0", seed=9, reverse_team1_actions=True)
+    env_b = GridworldCtfGPU(**ec, num_envs=B, device="cuda:0", seed=9, reverse_team1_actions=True, packed_obs=True)
+    dense = collect_rollout(env_a, agent, opponent, num_env_steps=T)
+    packed = collect_rollout(env_b, agent, opponent, num_env_steps=T, obs_storage_dtype="packed")
+    assert packed.packed and packed.grid_states.dtype == torch.int32
+    assert packed.grid_states.numel() * 4 * 31 < dense.grid_states.numel() * 4  # > 31x smaller
+    assert torch.equal(packed.unpack_grid_states(env_b), dense.grid_states)
+    mb = torch.tensor([5, 77, 120, 3], device="cuda")
+    assert torch.equal(packed.unpack_grid_states(env_b, mb, dtype=torch.bfloat16).float(), dense.grid_states[mb])
+    assert torch.equal(packed.actions, dense.actions) and torch.equal(packed.rewards, dense.rewards)
+
+
 def test_batched_duel_matches_reference_loop():
     from marl_ctf_development_b200 import GridworldCtfGPU
     from marl_ctf_development_b200.rollout import batched_duel

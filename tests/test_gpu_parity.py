@@ -424,3 +424,58 @@ def test_step_is_cuda_graph_capturable():
     se, sg = eager.get_state(), graphed.get_state()
     for k in STATE_KEYS + ("step", "stats"):
         assert np.array_equal(se[k], sg[k]), k
+
+
+def _pack_reference(obs_u8, wpa):
+    """numpy restatement of the packed layout: bit e of an agent's C*G*G block -> bit e % 32 of word e // 32."""
+    lead = obs_u8.shape[:-3]
+    flat = obs_u8.reshape(lead + (-1,))
+    pad = wpa * 32 - flat.shape[-1]
+    flat = np.concatenate([flat, np.zeros(lead + (pad,), dtype=np.uint8)], axis=-1)
+    return np.packbits(flat, axis=-1, bitorder="little").view("<u4").astype(np.int64)
+
+
+@pytest.mark.parametrize("exp", ["8_arena", "7_gridlocked", "0_the_split"])
+def test_packed_observations_and_unpack_round_trip(exp):
+    """obs_bits == packbits(standardise_state) per agent, and ctf_unpack_obs gives the dense tensors back in every dtype."""
+    B = 70
+    env = _env(exp, B, seed=31, packed_obs=True)
+    orc = OracleBatch(env.ce, B, seed=31)
+    rng = np.random.default_rng(5)
+    pol = traces.make_policy("builder", env.ce)
+    for t in range(45):
+        st = orc.state()
+        a = np.stack([pol(rng, st["pos"][b], st["has_flag"][b]) for b in range(B)])
+        env.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+        if t % 11 == 0:
+            o_ref, _ = orc.observe(u8=True)
+            want = _pack_reference(o_ref, env.bits_words_per_agent)
+            got = env.obs_bits.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            assert np.array_equal(got, want), f"{exp} t={t}: packed observations differ"
+            assert np.array_equal(env.obs.cpu().numpy(), o_ref.astype(np.float32))
+    for dtype in (torch.float32, torch.uint8, torch.float16, torch.bfloat16):
+        dense = env.unpack_obs(env.obs_bits, dtype=dtype)
+        assert tuple(dense.shape) == tuple(env.obs.shape) and dense.dtype == dtype
+        assert torch.equal(dense.float(), env.obs)
+    # a gathered minibatch with an odd number of blocks and an unaligned output slice
+    idx = torch.tensor([3, 17, 4, 60, 9], device="cuda")
+    mb = env.obs_bits[idx][:, 1:]
+    big = torch.zeros((mb.shape[0] * mb.shape[1] * env.n_channels * env.GRID_SIZE**2 + 3,), device="cuda")
+    view = big[3:].view(mb.shape[0], mb.shape[1], env.n_channels, env.GRID_SIZE, env.GRID_SIZE)
+    env.unpack_obs(mb, out=view)
+    assert torch.equal(view, env.obs[idx][:, 1:]) and float(big[:3].abs().sum()) == 0.0
+
+
+def test_packed_only_env_skips_the_dense_buffer():
+    B = 40
+    dense = _env("8_arena", B, seed=32)
+    packed = _env("8_arena", B, seed=32, packed_obs=True, dense_obs=False)
+    assert packed.obs is None
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for _ in range(30):
+        a = torch.randint(0, 9, (B, 8), dtype=torch.uint8, device="cuda", generator=gen)
+        dense.step(a)
+        packed.step(a)
+    assert torch.equal(packed.unpack_obs(packed.obs_bits), dense.obs)
+    assert torch.equal(packed.meta, dense.meta) and torch.equal(packed.rewards, dense.rewards)
