@@ -213,7 +213,8 @@ def run_ours(args) -> dict | None:
     ec = experiment_env_config(EXPERIMENT)
     env = GridworldCtfGPU(**ec, num_envs=B, device=dev, seed=args.seed, env_id_base=rank * B,
                           stats="none" if args.no_stats else "counters",
-                          obs_dtype=getattr(torch, args.obs_dtype))
+                          obs_dtype=getattr(torch, args.obs_dtype), packed_obs=args.packed or args.no_dense,
+                          dense_obs=not args.no_dense)
     N, G, C = env.N_AGENTS, env.GRID_SIZE, env.n_channels
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 8  # distinct pre-generated action tensors, resident in HBM before the timed region
@@ -294,6 +295,10 @@ def run_ours(args) -> dict | None:
         agent_steps = world * B * N * K
         value = agent_steps / (ms * 1e-3)
         per_agent_step = algorithmic_bytes_per_agent_step(G, N, C, {"float32": 4, "uint8": 1}.get(args.obs_dtype, 2))
+        if args.no_dense:
+            per_agent_step -= C * G * G * {"float32": 4, "uint8": 1}.get(args.obs_dtype, 2)
+        if args.packed or args.no_dense:
+            per_agent_step += env.bits_words_per_agent * 4
         launch_s = ms * 1e-3 / K
         achieved = per_agent_step * B * N / launch_s / 1e9
         peak, peak_src = measured_hbm_peak()
@@ -302,7 +307,8 @@ def run_ours(args) -> dict | None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": dict(workload_config(B, world), obs_dtype=args.obs_dtype),
+            "config": dict(workload_config(B, world), obs_dtype=args.obs_dtype,
+                           observation_outputs=("packed only" if args.no_dense else "dense + packed" if args.packed else "dense")),
             "clocks": clocks,
             "e2e": {
                 "value": world * B * N * Ke / (e2e_ms * 1e-3), "unit": UNIT,
@@ -338,6 +344,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-stats", action="store_true", help="skip the episode-statistics counters")
+    ap.add_argument("--packed", action="store_true", help="side measurement: also write the packed (1 bit/element) observation copy")
+    ap.add_argument("--no-dense", action="store_true", help="side measurement: packed observations only (implies --packed)")
     ap.add_argument("--graph-steps", type=int, default=0,
                     help="side measurement: replay a CUDA graph of this many captured steps (launch-bound small batches)")
     ap.add_argument("--experiment", default="8_arena", help="experiment config (side measurements; the headline is 8_arena)")
