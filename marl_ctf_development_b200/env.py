@@ -384,6 +384,20 @@ class GridworldCtfGPU:
         self._agents.copy_(torch.from_numpy(rec.view(np.int64)))
         self._envs.copy_(torch.from_numpy(envs.astype(np.uint32).view(np.int32)))
 
+    def flag_captures(self) -> torch.Tensor:
+        """metrics['team_flag_captures'] of every env: int64 [B, 2] (device)."""
+        return self._envs[:, 2:4].long()
+
+    def step_counts(self) -> torch.Tensor:
+        """env_step_count of every env: int64 [B] (device)."""
+        return self._envs[:, 0].long()
+
+    def counters(self) -> torch.Tensor:
+        """Per-env agent-level statistics, int64 [B, 13, N] in ctf_metric order (needs stats != 'none')."""
+        if self._stats is None:
+            raise RuntimeError("create the env with stats='counters' or 'full'")
+        return self._stats.long()
+
     # ------------------------------------------------------------------ episode statistics (env.metrics schema)
     def stats_sum(self, all_reduce=True) -> torch.Tensor:
         """int64 [13, N]: counters summed over this rank's envs, then over ranks (NCCL) when torch.distributed is up."""

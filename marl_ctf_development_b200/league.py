@@ -47,11 +47,12 @@ def duel_pairs(env_config: dict, pairs, duels_per_pair: int, max_steps: int = 25
         obs, meta, _, _, _ = env.step(actions)
         if step_count > max_steps or step_count >= env.GAME_STEPS:
             break
-    caps = env._envs[:, 2:4].long()
+    caps = env.flag_captures()
     results = torch.sign(caps[:, 0] - caps[:, 1]).reshape(P, D)
     metrics = None
     if collect_metrics:
-        per_pair = env._stats.long().reshape(P, D, *env._stats.shape[1:]).sum(1).cpu().numpy()
+        c = env.counters()
+        per_pair = c.reshape(P, D, *c.shape[1:]).sum(1).cpu().numpy()
         metrics = [metrics_dict(env.ce, per_pair[p]) for p in range(P)]
     env.close()
     return results, metrics

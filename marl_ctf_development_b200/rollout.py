@@ -155,6 +155,6 @@ def batched_duel(env, agent, opponent, max_steps=256, return_result=True):
         if step_count > max_steps or step_count >= env.GAME_STEPS:  # all envs finish in lock-step
             break
     if return_result:
-        caps = env._envs[:, 2:4].long()
+        caps = env.flag_captures()
         return torch.sign(caps[:, 0] - caps[:, 1])
     return env.episode_stats()
