@@ -36,6 +36,17 @@ class Rollout:
     next_done: torch.Tensor        # [B]
     packed: bool = False
 
+    def as_reference_arrays(self):
+        """The eleven values ``train_ppo`` keeps per update (ppo.py:298-305, 362-376), in the reference's order.
+
+        The first eight are already ``[num_steps, num_envs, ...]``.  The reference overwrites next_grid_state /
+        next_metadata_state / next_done with those of the *last* rollout only (ppo.py:372-374) and bootstraps every
+        env from that one value; the last env's row is returned to reproduce it — use the full ``next_*`` tensors
+        for a per-env bootstrap instead.
+        """
+        return (self.grid_states, self.metadata_states, self.actions, self.use_action_mask, self.logprobs, self.rewards,
+                self.dones, self.values, self.next_grid_state[-1:], self.next_metadata_state[-1:], self.next_done[-1:])
+
     def unpack_grid_states(self, env, index=slice(None), dtype=torch.float32) -> torch.Tensor:
         """grid_states[index] as [..., C, G, G] of ``dtype`` — expands packed storage with the CUDA unpack kernel
         (the PPO update gathers minibatches this way, ppo.py:440-449, without a float32 rollout buffer)."""

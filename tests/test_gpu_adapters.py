@@ -88,6 +88,9 @@ def test_batched_rollout_matches_reference_loop(train_team1):
     assert float(ro.dones.abs().sum()) == 0.0  # never written by the reference (ppo.py:53)
     apt = env.N_AGENTS // 2
     assert tuple(ro.grid_states.shape) == (T * apt, B, env.n_channels, env.GRID_SIZE, env.GRID_SIZE)
+    arrays = ro.as_reference_arrays()   # ppo.py:298-305 / 362-376 order and shapes
+    assert len(arrays) == 11 and tuple(arrays[8].shape) == (1, env.n_channels, env.GRID_SIZE, env.GRID_SIZE)
+    assert tuple(arrays[5].shape) == (T * apt, B) and tuple(arrays[10].shape) == (1,)
 
 
 def test_rollout_with_packed_observation_storage():
