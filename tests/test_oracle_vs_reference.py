@@ -164,3 +164,41 @@ def test_random_scenarios_and_configs(seed):
             assert np.array_equal(ro, oo), (seed, t)
             assert np.array_equal(bits(rm), bits(om)), (seed, t, rm, om)
     assert np.array_equal(rs.agent_metrics(ref), orc.state()["stats"])
+
+
+def test_metrics_dict_feeds_the_reference_metrics_logger():
+    """env.metrics rebuilt from the agent-level counters (metrics_dict) is harvested by the reference's
+    MetricsLogger (metrics_logger.py:137-159) exactly like the reference env's own dict."""
+    import importlib
+
+    from marl_ctf_development_b200.env import metrics_dict
+
+    rs.reference_modules()
+    ml = importlib.import_module("metrics_logger")
+    ec = rs.experiment_env_config("8_arena")
+    ce = compile_config(**ec)
+    ref = rs.make_injected_env(ec, seed=5, env_id=5)
+    orc = OracleEnv(ce, seed=5, env_id=5)
+    pol = traces.make_policy("seek", ce)
+    rng = np.random.default_rng(2)
+    for t in range(300):
+        s = rs.snapshot(ref, ce.cfg.hp_scale)
+        a = pol(rng, s["pos"], s["has_flag"])
+        ref.step(a.tolist())
+        orc.step(a)
+    ours = metrics_dict(ce, orc.state()["stats"], orc.state()["visits"])
+    team_types = {t: sorted({ce.AGENT_TYPES[i] for i in range(ce.N_AGENTS) if ce.AGENT_TEAMS[i] == t}) for t in (0, 1)}
+    loggers = []
+    for metrics in (ref.metrics, ours):
+        lg = ml.MetricsLogger(1, 0, 0, team_types, list(range(ce.N_AGENTS)), symmetric_teams=False)
+        lg.harvest_metrics(metrics, "t0_m0", 0, 0.5, team_idx=0)
+        lg.harvest_metrics(metrics, "t1_m0", 0, 0.25, team_idx=1)
+        loggers.append(lg)
+    a, b = loggers
+    for label in ("t0_m0", "t1_m0"):
+        for metric, val in a.metrics[label].items():
+            if isinstance(val, list):
+                assert val == b.metrics[label][metric], (label, metric)
+            else:
+                assert {k: v for k, v in val.items()} == {k: v for k, v in b.metrics[label][metric].items()}, (label, metric)
+    assert a.metrics["t0_m0"]["team_steps_adj_teammate"][0] > 0  # something was actually harvested
