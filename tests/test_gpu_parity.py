@@ -479,3 +479,36 @@ def test_packed_only_env_skips_the_dense_buffer():
         packed.step(a)
     assert torch.equal(packed.unpack_obs(packed.obs_bits), dense.obs)
     assert torch.equal(packed.meta, dense.meta) and torch.equal(packed.rewards, dense.rewards)
+
+
+@pytest.mark.parametrize("exp,B", [("8_arena", 2048), ("7_gridlocked", 2048), ("0_the_split", 4096)])
+def test_soak_three_episodes_with_resets(exp, B):
+    """Long differential run: 3 episodes x 500 steps with resets in between, flag-seeking/builder actions, every reward
+    and done compared each step, full state + observations + statistics at checkpoints.  Rare paths must have fired."""
+    seed = 33
+    env = _env(exp, B, seed=seed, stats="counters")
+    orc = OracleBatch(env.ce, B, seed=seed)
+    rng = np.random.default_rng(seed)
+    totals = np.zeros((13,), dtype=np.int64)
+    for episode in range(3):
+        if episode:
+            env.reset()
+            orc.reset()
+        for t in range(500):
+            st = orc.state() if t % 1 == 0 else st
+            a = traces.seek_actions_batch(rng, env.ce, st["pos"], st["has_flag"], eps=0.3 + 0.1 * episode, second_p=0.3 + 0.15 * episode)
+            _, _, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+            r_ref, d_ref = orc.step(a)
+            if t % 5 == 0 or t >= 497:
+                assert np.array_equal(bits(rew.cpu().numpy()), bits(r_ref)), f"{exp} ep{episode} t={t}: rewards differ"
+                assert np.array_equal(done.cpu().numpy(), d_ref)
+            if t % 100 == 99:
+                _assert_batch_state(env, orc, f"{exp} ep{episode} t={t}")
+                _assert_obs(env, orc, f"{exp} ep{episode} t={t}")
+        so = orc.state()
+        assert np.array_equal(env.get_state()["stats"], so["stats"]), f"{exp} ep{episode}: statistics differ"
+        totals += so["stats"].sum(0).sum(1)
+    # tag, respawn, pickup, capture, dispossession fired in every scenario; mining / placing where miners exist
+    assert (totals[:5] > 0).all(), totals
+    if 3 in env.AGENT_TYPES.values():
+        assert totals[5] > 0 and totals[6] > 0, totals

@@ -61,3 +61,23 @@ OBS_EVERY = 20
 def snap_after_step(t: int, env_step: int, game_steps: int) -> bool:
     """Whether the golden traces hold an observation after recorded step t (t counts from 1)."""
     return t % OBS_EVERY == 0 or env_step in (game_steps - 1, game_steps, game_steps + 1)
+
+
+def seek_actions_batch(rng, ce, pos, has_flag, eps=0.25, second_p=0.35) -> np.ndarray:
+    """Vectorised seek policy for a whole batch: pos [B,N,2], has_flag [B,N] -> uint8 [B,N] (soak tests)."""
+    pos = np.asarray(pos, dtype=np.int64)
+    B, N = pos.shape[0], ce.N_AGENTS
+    teams = np.array([ce.AGENT_TEAMS[i] for i in range(N)])
+    types = np.array([ce.AGENT_TYPES[i] for i in range(N)])
+    flags = np.array([ce.FLAG_POSITIONS[0], ce.FLAG_POSITIONS[1]], dtype=np.int64)
+    target = np.where(np.asarray(has_flag, dtype=bool)[..., None], flags[teams][None], flags[1 - teams][None])
+    d = target - pos
+    # candidate unit moves toward the target: U, D, R, L
+    want = np.stack([d[..., 0] < 0, d[..., 0] > 0, d[..., 1] > 0, d[..., 1] < 0], axis=-1)
+    score = np.where(want, rng.random((B, N, 4)), -1.0)
+    a = np.where(want.any(-1), score.argmax(-1), 4)
+    second = (a < 4) & np.isin(types, (2, 3))[None] & (rng.random((B, N)) < second_p)
+    a = np.where(second, a + 5, a)
+    rnd = rng.random((B, N)) < eps
+    a = np.where(rnd, rng.integers(0, 9, (B, N)), a)
+    return a.astype(np.uint8)
