@@ -639,16 +639,18 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
     // ---- rewards (:727-730, :873, :957-966, :920-940) in fp64, stored as fp32 (ppo.py:108)
     const bool done = step >= P.game_steps;   // set at step == GAME_STEPS and never cleared until reset (:914-915)
     {
+        // every operation is a separately rounded IEEE add / multiply (__dadd_rn / __dmul_rn are never contracted
+        // into an FMA): -0.5 + 5 * 0.1 must give the reference's exact 0.0, not the fused 2.8e-17
         double r = 0.0;
-        r += P.reward_step;
-        if (captured) r += P.reward_capture;
-        if (tag_reward) r += P.reward_tag;
-        if (P.use_adjusted_rewards && ((cap_team >> (1 - my_team)) & 1u)) r -= P.capture_punish;
+        r = __dadd_rn(r, P.reward_step);
+        if (captured) r = __dadd_rn(r, P.reward_capture);
+        if (tag_reward) r = __dadd_rn(r, P.reward_tag);
+        if (P.use_adjusted_rewards && ((cap_team >> (1 - my_team)) & 1u)) r = __dadd_rn(r, -P.capture_punish);
         if (step == P.game_steps && caps0 != caps1) {
-            const int margin = abs(caps0 - caps1);
+            const double margin = (double)abs(caps0 - caps1);
             const int winner = caps0 > caps1 ? 0 : 1;
-            if (my_team == winner) r += margin * P.win_margin;
-            else r -= margin * P.loss_margin;
+            if (my_team == winner) r = __dadd_rn(r, __dmul_rn(margin, P.win_margin));
+            else r = __dadd_rn(r, -__dmul_rn(margin, P.loss_margin));
         }
         if (L.rewards && lane < N) L.rewards[env * N + lane] = (float)r;
     }

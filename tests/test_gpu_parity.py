@@ -512,3 +512,35 @@ def test_soak_three_episodes_with_resets(exp, B):
     assert (totals[:5] > 0).all(), totals
     if 3 in env.AGENT_TYPES.values():
         assert totals[5] > 0 and totals[6] > 0, totals
+
+
+def test_terminal_reward_is_not_fused_multiply_add():
+    """Regression found by the soak test: a punished agent of the winning team at the terminal step gets
+    -0.5 + margin * 0.1 with two roundings (exactly 0.0 for margin 5), never an FMA (2.8e-17)."""
+    B = 8
+    env = _env("8_arena", B, seed=1, stats="none")
+    orc = OracleBatch(env.ce, B, seed=1)
+    so = orc.state()
+    grid, pos, flag = so["grid"].copy(), so["pos"].copy(), so["has_flag"].copy()
+    # agent 7 (team 1 scout) stands two cells above its own flag (12, 7) carrying team 0's flag
+    for b in range(B):
+        r, c = pos[b, 7]
+        grid[b, r, c] = 0
+        pos[b, 7] = (10, 7)
+        grid[b, 10, 7] = 8          # team-1 scout tile
+        grid[b, 2, 7] = 1           # team 0's flag cell holds a block tile while the flag is carried (:587)
+        flag[b, 7] = 1
+    so["step"][:] = 499
+    caps = np.tile(np.array([[6, 0]]), (B, 1))
+    caps[1] = (3, 0)
+    caps[2] = (8, 0)
+    args = (grid, pos, so["hp_q"], flag, so["inventory"], so["step"], so["episode"], caps)
+    orc.set_state(*args)
+    env.set_state(*args)
+    a = np.full((B, 8), 4, dtype=np.uint8)
+    a[:, 7] = 1                     # D: (10,7) -> (11,7), within 1 of the own flag -> capture
+    _, _, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+    r_ref, d_ref = orc.step(a)
+    assert orc.state()["captures"][0].tolist() == [6, 1] and bool(d_ref.all())
+    assert r_ref[0, 0] == 0.0 and r_ref[0, 7] == 1.0       # -0.5 + 5 * 0.1 == 0.0 exactly in the reference
+    assert np.array_equal(bits(rew.cpu().numpy()), bits(r_ref)), (rew.cpu().numpy(), r_ref)
