@@ -28,6 +28,13 @@ KWARG_CASES = [
     ("uneven_teams", "8_arena", {"AGENT_CONFIG": _agents([0, 1, 2, 3, 1, 2], teams=[0, 0, 0, 0, 1, 1]), "MAP_SYMMETRY_CHECK": False}, "seek"),
     ("four_scouts_tiny_tile_set", "0_the_split", {"AGENT_CONFIG": _agents([0, 0, 0, 0]), "MAP_SYMMETRY_CHECK": False}, "seek"),
     ("all_miners", "2_jailbreak", {"AGENT_CONFIG": _agents([3, 3, 3, 3]), "MAP_SYMMETRY_CHECK": False}, "builder"),
+    # every hit is lethal and always lands: respawn storms, several lethal hits in one actor's turn, carriers killed
+    ("one_hit_kills_arena", "8_arena", {"TAG_PROBABILITY": 1.0, "AGENT_TYPE_HP": {0: 1, 1: 1, 2: 1, 3: 1},
+                                        "AGENT_TYPE_DAMAGE": {0: 1, 1: 1, 2: 1, 3: 1}, "VAULT_MIN_HP": 0.0, "VAULT_HP_COST": 0.25}, "seek"),
+    ("one_hit_kills_split", "0_the_split", {"TAG_PROBABILITY": 1.0, "AGENT_TYPE_HP": {0: 0.5, 1: 0.5, 2: 0.5, 3: 0.5},
+                                            "AGENT_TYPE_DAMAGE": {0: 0.5, 1: 0.25, 2: 0.5, 3: 0.5}, "GUARDIAN_DAMAGE_MULTIPLIER": 2.0}, "seek"),
+    ("glass_cannons_gridlocked", "7_gridlocked", {"TAG_PROBABILITY": 0.9, "AGENT_TYPE_HP": {0: 1.5, 1: 1, 2: 2, 3: 1},
+                                                  "AGENT_TYPE_DAMAGE": {0: 1, 1: 0.5, 2: 1, 3: 2}, "AGENT_HP_HEALING_PER_STEP": 0.5}, "builder"),
 ]
 
 CASE_IDS = [c[0] for c in KWARG_CASES]

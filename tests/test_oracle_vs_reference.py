@@ -202,3 +202,39 @@ def test_metrics_dict_feeds_the_reference_metrics_logger():
             else:
                 assert {k: v for k, v in val.items()} == {k: v for k, v in b.metrics[label][metric].items()}, (label, metric)
     assert a.metrics["t0_m0"]["team_steps_adj_teammate"][0] > 0  # something was actually harvested
+
+
+def test_multi_lethal_turns_and_carrier_kills_match_the_reference():
+    """One-hit-kill settings for 4 episodes: several lethal hits inside one actor's turn (chained respawns whose
+    windows depend on each other) and killed flag carriers must have happened, and match step by step."""
+    name, exp, overrides, kind = [c for c in KWARG_CASES if c[0] == "one_hit_kills_arena"][0]
+    ec = build_env_config(rs.experiment_env_config(exp), overrides)
+    ec["GAME_STEPS"] = 400
+    ce = compile_config(**ec)
+    ref = rs.make_injected_env(ec, seed=606, env_id=9)
+    orc = OracleEnv(ce, seed=606, env_id=9)
+    rng = np.random.default_rng(4)
+    multi_lethal, carrier_kills = 0, 0
+    for episode in range(4):
+        if episode:
+            ref.reset()
+            orc.reset()
+        prev = np.zeros((13, ce.N_AGENTS), dtype=np.int64)
+        for t in range(400):
+            s = rs.snapshot(ref, ce.cfg.hp_scale)
+            a = traces.seek_actions_batch(rng, ce, s["pos"][None], s["has_flag"][None], eps=0.15)[0]
+            _, rr, rd = ref.step(a.tolist())
+            orr, od = orc.step(a)
+            st = orc.state()
+            assert_state_equal(st, rs.snapshot(ref, ce.cfg.hp_scale), f"ep{episode} t={t}")
+            assert np.array_equal(bits(np.array(rr, dtype=np.float32)), bits(orr)) and rd == od
+            cur = st["stats"]
+            multi_lethal += int(((cur[1] - prev[1]) >= 2).sum())
+            carrier_kills += int((cur[4] - prev[4]).sum())
+            prev = cur
+            if t % 20 == 0:
+                ro, rm = rs.observations(ref)
+                oo, om = orc.observe()
+                assert np.array_equal(ro, oo) and np.array_equal(bits(rm), bits(om))
+        assert np.array_equal(rs.agent_metrics(ref), orc.state()["stats"])
+    assert multi_lethal >= 2 and carrier_kills >= 10, (multi_lethal, carrier_kills)
