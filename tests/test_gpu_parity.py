@@ -481,12 +481,17 @@ def test_packed_only_env_skips_the_dense_buffer():
     assert torch.equal(packed.meta, dense.meta) and torch.equal(packed.rewards, dense.rewards)
 
 
-@pytest.mark.parametrize("exp,B", [("8_arena", 2048), ("7_gridlocked", 2048), ("0_the_split", 4096)])
-def test_soak_three_episodes_with_resets(exp, B):
+def _case_overrides(name):
+    return dict([c for c in KWARG_CASES if c[0] == name][0][2])
+
+
+@pytest.mark.parametrize("exp,B,case", [("8_arena", 2048, None), ("7_gridlocked", 2048, None), ("0_the_split", 4096, None),
+                                        ("8_arena", 2048, "one_hit_kills_arena"), ("7_gridlocked", 1024, "glass_cannons_gridlocked")])
+def test_soak_three_episodes_with_resets(exp, B, case):
     """Long differential run: 3 episodes x 500 steps with resets in between, flag-seeking/builder actions, every reward
     and done compared each step, full state + observations + statistics at checkpoints.  Rare paths must have fired."""
     seed = 33
-    env = _env(exp, B, seed=seed, stats="counters")
+    env = _env(exp, B, seed=seed, stats="counters", env_overrides=_case_overrides(case) if case else {})
     orc = OracleBatch(env.ce, B, seed=seed)
     rng = np.random.default_rng(seed)
     totals = np.zeros((13,), dtype=np.int64)
