@@ -549,3 +549,36 @@ def test_terminal_reward_is_not_fused_multiply_add():
     assert orc.state()["captures"][0].tolist() == [6, 1] and bool(d_ref.all())
     assert r_ref[0, 0] == 0.0 and r_ref[0, 7] == 1.0       # -0.5 + 5 * 0.1 == 0.0 exactly in the reference
     assert np.array_equal(bits(rew.cpu().numpy()), bits(r_ref)), (rew.cpu().numpy(), r_ref)
+
+
+def test_visitation_maps_wrap_and_non_default_stream():
+    """uint8 visitation maps wrap at 256 (standing still for 300 steps); the same run on a side stream gives the same state."""
+    B = 33
+    a = torch.full((B, 4), 4, dtype=torch.uint8, device="cuda")
+    env0 = _env("0_the_split", B, seed=3, stats="full")
+    orc = OracleBatch(env0.ce, B, seed=3)
+    side = torch.cuda.Stream()
+    env1 = _env("0_the_split", B, seed=3, stats="full")
+    for t in range(300):
+        env0.step(a)
+        orc.step(a.cpu().numpy())
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for t in range(300):
+            env1.step(a)
+    side.synchronize()
+    torch.cuda.synchronize()
+    s0, s1, so = env0.get_state(), env1.get_state(), orc.state()
+    assert np.array_equal(s0["visits"], so["visits"]) and int(s0["visits"].max()) == 301 % 256
+    for k in STATE_KEYS + ("stats", "visits", "step"):
+        assert np.array_equal(s0[k], s1[k]), k
+    assert torch.equal(env0.obs, env1.obs)
+
+
+def test_closed_env_fails_loudly():
+    from marl_ctf_development_b200._native import NativeError
+
+    env = _env("0_the_split", 4, seed=1)
+    env.close()
+    with pytest.raises(NativeError):
+        env.step(torch.zeros((4, 4), dtype=torch.uint8, device="cuda"))

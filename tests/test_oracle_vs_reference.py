@@ -238,3 +238,18 @@ def test_multi_lethal_turns_and_carrier_kills_match_the_reference():
                 assert np.array_equal(ro, oo) and np.array_equal(bits(rm), bits(om))
         assert np.array_equal(rs.agent_metrics(ref), orc.state()["stats"])
     assert multi_lethal >= 2 and carrier_kills >= 10, (multi_lethal, carrier_kills)
+
+
+def test_visitation_maps_wrap_at_256_like_numpy_uint8():
+    """Agents that stand still for 300 steps: the reference's uint8 visitation maps overflow and wrap (gridworld_ctf.py:469, :486)."""
+    ec = rs.experiment_env_config("0_the_split")
+    ce = compile_config(**ec)
+    ref = rs.make_injected_env(ec, seed=1, env_id=1)
+    orc = OracleEnv(ce, seed=1, env_id=1)
+    a = np.full(ce.N_AGENTS, 4, dtype=np.uint8)
+    for t in range(300):
+        ref.step(a.tolist())
+        orc.step(a)
+    vm = np.stack([ref.metrics["agent_visitation_maps"][i] for i in range(ce.N_AGENTS)])
+    assert np.array_equal(vm, orc.state()["visits"])
+    assert vm.max() == (301 % 256)  # 1 at reset + 300 steps, wrapped
