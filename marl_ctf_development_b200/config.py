@@ -196,8 +196,10 @@ def compile_config(
     n = len(AGENT_CONFIG)
     if not (1 <= n <= MAX_AGENTS):
         raise ValueError(f"N_AGENTS must be in 1..{MAX_AGENTS}, got {n}")
-    if sorted(AGENT_CONFIG.keys()) != list(range(n)):
-        raise ValueError("AGENT_CONFIG keys must be 0..N-1")
+    if list(AGENT_CONFIG.keys()) != list(range(n)):
+        # the reference derives OPPONENTS, TILES_USED and the metadata HP slots from the dict's insertion order
+        # (gridworld_ctf.py:203-206, 393-394, 1040): only the ordered form 0..N-1 used by every experiment is supported
+        raise ValueError("AGENT_CONFIG keys must be 0..N-1 in that order")
     g = int(SCENARIO["GRID_SIZE"])  # load_scenario overrides the ctor's GRID_SIZE (:359)
     if not (2 <= g <= MAX_GRID):
         raise ValueError(f"GRID_SIZE must be in 2..{MAX_GRID}, got {g}")

@@ -100,6 +100,9 @@ def test_rejects_what_the_reference_cannot_run():
         compile_config(**{**ec, "AGENT_CONFIG": two})  # get_env_metadata reads agent_hp[3] (gridworld_ctf.py:1041)
     with pytest.raises(ValueError):
         compile_config(**{**ec, "AGENT_HP_HEALING_PER_STEP": 0.1})  # not a dyadic rational
+    shuffled = {1: {"team": 1, "type": 0}, 0: {"team": 0, "type": 0}}
+    with pytest.raises(ValueError):
+        compile_config(**{**ec, "AGENT_CONFIG": shuffled})  # insertion order matters in the reference
 
 
 def test_default_hp_configs_compile():
