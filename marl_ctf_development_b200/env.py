@@ -487,16 +487,21 @@ class GridworldCtf:
         return self.grid, r, bool(dones[0].item())
 
     def standardise_state(self, agent_idx, reverse_grid=False):
-        key = ("obs", bool(reverse_grid))
+        i, rev = int(agent_idx), bool(reverse_grid)
+        if rev == (self.AGENT_TEAMS[i] != 0):
+            # the view every caller asks for (ppo.py:69/87, utils.py:535): already written by the last step / reset
+            if "canonical" not in self._cache:
+                self._cache["canonical"] = self._gpu.obs[0].cpu().numpy()
+            return self._cache["canonical"][i][None].copy()
+        key = ("obs", rev)
         if key not in self._cache:
-            obs, _ = self._gpu.observe(reverse_flags=[int(bool(reverse_grid))] * self.N_AGENTS, into_new=True)
+            obs, _ = self._gpu.observe(reverse_flags=[int(rev)] * self.N_AGENTS, into_new=True)
             self._cache[key] = obs[0].cpu().numpy()
-        return self._cache[key][int(agent_idx)][None].copy()
+        return self._cache[key][i][None].copy()
 
     def get_env_metadata(self, agent_idx):
         if "meta" not in self._cache:
-            _, meta = self._gpu.observe(into_new=True)
-            self._cache["meta"] = meta[0].cpu().numpy()
+            self._cache["meta"] = self._gpu.meta[0].cpu().numpy()  # written by the last step / reset
         return self._cache["meta"][int(agent_idx)].astype(np.float16)[None]
 
     def get_env_dims(self):
