@@ -245,16 +245,23 @@ class GridworldCtfGPU:
 
         ``actions`` is the static uint8 [B, N] device tensor the caller refills before each replay (with
         steps_per_replay > 1 the same actions are applied every step — useful for no-op/benchmark loops only).
+        The env state is unchanged by this call (the warm-up launch runs on a snapshot); the output buffers
+        (obs / meta / rewards / dones) are overwritten.
         Returns the ``torch.cuda.CUDAGraph``; call ``.replay()``.  ctf_step makes no allocation and no host
         synchronisation, so it is capturable as is; a policy forward can be captured in the same graph by the caller.
         """
         a = self._as_actions(actions)
         if a.data_ptr() != actions.data_ptr():
             raise ValueError("actions must already be a contiguous uint8 [B, N] tensor on the env's device")
+        # warm-up launch outside the capture, on a snapshot so that the env does not advance
+        state = [t for t in (self._grid, self._agents, self._envs, self._stats, self._visits) if t is not None]
+        saved = [t.clone() for t in state]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self.step(a)  # warm-up outside capture
+            self.step(a)
+            for t, s_ in zip(state, saved):
+                t.copy_(s_)
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -321,7 +328,8 @@ class GridworldCtfGPU:
         if tuple(actions.shape) != (self.num_envs, self.N_AGENTS):
             raise ValueError(f"actions must have shape {(self.num_envs, self.N_AGENTS)}, got {tuple(actions.shape)}")
         if actions.dtype != torch.uint8:
-            actions = actions.clamp(0, 255).to(torch.uint8)
+            # anything outside 0..8 (KeyError in the reference) becomes 255 so that the device fault bit fires
+            actions = torch.where((actions < 0) | (actions > 8), torch.full_like(actions, 255), actions).to(torch.uint8)
         return actions.to(self.device, non_blocking=True).contiguous()
 
     def raise_on_faults(self):

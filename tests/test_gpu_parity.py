@@ -315,6 +315,11 @@ def test_out_of_range_action_faults_like_keyerror():
     a[3, 1] = 9
     with pytest.raises(KeyError):
         env.step(a)
+    for bad in (-1, 300):          # wider integer inputs: out-of-range values must not be folded into valid actions
+        b = torch.full((8, env.N_AGENTS), 4, dtype=torch.int64, device="cuda")
+        b[0, 0] = bad
+        with pytest.raises(KeyError):
+            env.step(b)
 
 
 def test_observe_with_explicit_reverse_flags_and_symmetry():
@@ -411,10 +416,8 @@ def test_step_is_cuda_graph_capturable():
     acts = torch.zeros((B, eager.N_AGENTS), dtype=torch.uint8, device="cuda")
     gen = torch.Generator(device="cuda").manual_seed(9)
     acts.copy_(torch.randint(0, 9, acts.shape, dtype=torch.uint8, device="cuda", generator=gen))
-    eager.step(acts)
-    graph = graphed.make_step_graph(acts)       # takes the same first step as its warm-up
-    eager.step(acts)                            # the capture itself does not execute: replay it once to stay aligned
-    graph.replay()
+    graph = graphed.make_step_graph(acts)       # leaves the env state untouched
+    assert int(graphed.step_counts().max()) == 0
     for _ in range(50):
         acts.copy_(torch.randint(0, 9, acts.shape, dtype=torch.uint8, device="cuda", generator=gen))
         eager.step(acts)
