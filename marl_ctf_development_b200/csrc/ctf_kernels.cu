@@ -35,6 +35,11 @@ namespace {
 // plain write-back stores are 4 % faster than .cs for this stream (L2 merges and schedules the write-backs).
 #define CTF_STORE_OP 1
 #endif
+#ifndef CTF_STATE_HINT
+// 1: env state loads / stores carry an L2 evict_last policy (and, with CTF_STORE_OP 3, the observation stream an
+// evict_first policy) so that the 22 MB of state written by step t are still in L2 when step t+1 reads them.
+#define CTF_STATE_HINT 0
+#endif
 constexpr int kWarpsPerCta = CTF_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kRow = 16;       // shared/global grid row stride (cells)
@@ -195,13 +200,62 @@ __device__ __forceinline__ __nv_bfloat16 from_bit<__nv_bfloat16>(uint32_t bit) {
     return __ushort_as_bfloat16((unsigned short)(bit ? 0x3F80u : 0u));
 }
 
+__device__ __forceinline__ uint64_t l2_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 __device__ __forceinline__ void store_vec(uint4* p, uint4 v) {
 #if CTF_STORE_OP == 0
     __stcs(p, v);
 #elif CTF_STORE_OP == 1
     *p = v;
-#else
+#elif CTF_STORE_OP == 2
     __stwt(p, v);
+#else
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+                 "l"(l2_evict_first()) : "memory");
+#endif
+}
+
+// env state accesses (tile map, agent records, env record)
+__device__ __forceinline__ uint4 ld_state(const uint4* p) {
+#if CTF_STATE_HINT
+    uint4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(l2_evict_last()));
+    return v;
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+#if CTF_STATE_HINT
+    unsigned long long v;
+    asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_evict_last()));
+    return v;
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ void st_state(uint4* p, uint4 v) {
+#if CTF_STATE_HINT
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+                 "l"(l2_evict_last()) : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+#if CTF_STATE_HINT
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(l2_evict_last()) : "memory");
+#else
+    *p = v;
 #endif
 }
 
@@ -345,15 +399,15 @@ __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int st
 __device__ __forceinline__ void store_state(const DevPlan& P, const Launch& L, const WarpMem& w, long long env,
                                             uint32_t me, int inv, uint4 ev, int lane) {
     if (lane < kGridBytes / 16)
-        reinterpret_cast<uint4*>(L.grid + env * kGridBytes)[lane] = reinterpret_cast<const uint4*>(w.grid)[lane];
+        st_state(reinterpret_cast<uint4*>(L.grid + env * kGridBytes) + lane, reinterpret_cast<const uint4*>(w.grid)[lane]);
     if (lane < P.N) {
         const unsigned long long rec = (unsigned long long)ag_r(me) | ((unsigned long long)ag_c(me) << 8) |
                                        ((unsigned long long)ag_flag(me) << 16) |
                                        ((unsigned long long)(uint16_t)ag_hp(me) << 32) |
                                        ((unsigned long long)(uint16_t)inv << 48);
-        L.agents[env * P.N + lane] = rec;
+        st_state(L.agents + env * P.N + lane, rec);
     }
-    if (lane == 0) L.envs[env] = ev;
+    if (lane == 0) st_state(L.envs + env, ev);
 }
 
 // Per-step counter deltas of this lane's agent, 4 bits per metric (every per-step increment is <= 15:
@@ -420,14 +474,14 @@ __global__ void __launch_bounds__(kThreads) k_observe(const __grid_constant__ De
     if (env >= L.B) return;
     const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw), warp);
     if (lane < kGridBytes / 16)
-        reinterpret_cast<uint4*>(w.grid)[lane] = reinterpret_cast<const uint4*>(L.grid + env * kGridBytes)[lane];
+        reinterpret_cast<uint4*>(w.grid)[lane] = ld_state(reinterpret_cast<const uint4*>(L.grid + env * kGridBytes) + lane);
     const int li = lane & 7;
     uint32_t me = 0;
     if (lane < P.N) {
-        const unsigned long long rec = L.agents[env * P.N + lane];
+        const unsigned long long rec = ld_state(L.agents + env * P.N + lane);
         me = pack_agent((int)(rec & 0xFF), (int)((rec >> 8) & 0xFF), (int)((rec >> 16) & 1), (int)(short)(rec >> 32));
     }
-    const uint4 ev = L.envs[env];
+    const uint4 ev = ld_state(L.envs + env);
     __syncwarp();
     const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
                                                         : __ballot_sync(kFull, lane < P.N && P.obs_rev[li]);
@@ -450,17 +504,17 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
 
     // ---- stage state: tile map -> shared memory, agent i -> lane i
     if (lane < kGridBytes / 16)
-        reinterpret_cast<uint4*>(w.grid)[lane] = reinterpret_cast<const uint4*>(L.grid + env * kGridBytes)[lane];
+        reinterpret_cast<uint4*>(w.grid)[lane] = ld_state(reinterpret_cast<const uint4*>(L.grid + env * kGridBytes) + lane);
     uint32_t me = 0;
     int inv = 0;
     int action = 4;
     if (lane < N) {
-        const unsigned long long rec = L.agents[env * N + lane];
+        const unsigned long long rec = ld_state(L.agents + env * N + lane);
         me = pack_agent((int)(rec & 0xFF), (int)((rec >> 8) & 0xFF), (int)((rec >> 16) & 1), (int)(short)(rec >> 32));
         inv = (int)((rec >> 48) & 0xFFFF);
         action = L.actions[env * N + lane];
     }
-    uint4 ev = L.envs[env];
+    uint4 ev = ld_state(L.envs + env);
     Deltas dl;
     const int my_team = P.team[li], my_type = P.type[li], my_slot = P.my_slot[li];
     const bool bad_action = lane < N && action >= CTF_N_ACTIONS;
