@@ -200,6 +200,7 @@ __device__ __forceinline__ __nv_bfloat16 from_bit<__nv_bfloat16>(uint32_t bit) {
     return __ushort_as_bfloat16((unsigned short)(bit ? 0x3F80u : 0u));
 }
 
+#if CTF_STATE_HINT || CTF_STORE_OP == 3
 __device__ __forceinline__ uint64_t l2_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -210,6 +211,7 @@ __device__ __forceinline__ uint64_t l2_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+#endif
 
 __device__ __forceinline__ void store_vec(uint4* p, uint4 v) {
 #if CTF_STORE_OP == 0
