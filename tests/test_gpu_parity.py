@@ -585,3 +585,25 @@ def test_closed_env_fails_loudly():
     env.close()
     with pytest.raises(NativeError):
         env.step(torch.zeros((4, 4), dtype=torch.uint8, device="cuda"))
+
+
+@pytest.mark.parametrize("exp", ["0_the_split", "1_fence", "2_jailbreak", "3_one_way_out", "4_keyhole", "5_skittles", "6_the_wall", "7_gridlocked", "8_arena"])
+def test_soak_every_experiment_full_episode_with_visits(exp):
+    """Every experiment script's config: 1 024 envs, one full episode + 2 steps past done, statistics and visitation maps."""
+    B, seed = 1024, 44
+    env = _env(exp, B, seed=seed, stats="full", obs_dtype=torch.uint8)
+    orc = OracleBatch(env.ce, B, seed=seed)
+    rng = np.random.default_rng(seed)
+    for t in range(env.GAME_STEPS + 2):
+        st = orc.state()
+        a = traces.seek_actions_batch(rng, env.ce, st["pos"], st["has_flag"], eps=0.35, second_p=0.5)
+        _, _, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+        r_ref, d_ref = orc.step(a)
+        if t % 4 == 0 or t >= env.GAME_STEPS - 2:
+            assert np.array_equal(bits(rew.cpu().numpy()), bits(r_ref)), f"{exp} t={t}: rewards differ"
+            assert np.array_equal(done.cpu().numpy(), d_ref)
+        if t % 125 == 124 or t >= env.GAME_STEPS - 1:
+            _assert_batch_state(env, orc, f"{exp} t={t}")
+            _assert_obs(env, orc, f"{exp} t={t}", u8=True)
+    st, so = env.get_state(), orc.state()
+    assert np.array_equal(st["stats"], so["stats"]) and np.array_equal(st["visits"], so["visits"])
