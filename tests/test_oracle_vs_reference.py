@@ -253,3 +253,28 @@ def test_visitation_maps_wrap_at_256_like_numpy_uint8():
     vm = np.stack([ref.metrics["agent_visitation_maps"][i] for i in range(ce.N_AGENTS)])
     assert np.array_equal(vm, orc.state()["visits"])
     assert vm.max() == (301 % 256)  # 1 at reset + 300 steps, wrapped
+
+
+@pytest.mark.parametrize("exp", rs.EXPERIMENTS)
+def test_full_episode_with_the_aggressive_policy(exp):
+    """Every experiment config for one whole episode (+2 steps past done) under the flag-seeking / second-action-heavy
+    policy the GPU soak tests use: captures, terminal margins, mining, placing and respawns all occur."""
+    ec = rs.experiment_env_config(exp)
+    ce = compile_config(**ec)
+    ref = rs.make_injected_env(ec, seed=808, env_id=3)
+    orc = OracleEnv(ce, seed=808, env_id=3)
+    rng = np.random.default_rng(8)
+    for t in range(ec["GAME_STEPS"] + 2):
+        s = rs.snapshot(ref, ce.cfg.hp_scale)
+        a = traces.seek_actions_batch(rng, ce, s["pos"][None], s["has_flag"][None], eps=0.35, second_p=0.5)[0]
+        _, rr, rd = ref.step(a.tolist())
+        orr, od = orc.step(a)
+        assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"{exp} t={t}")
+        assert np.array_equal(bits(np.array(rr, dtype=np.float32)), bits(orr)) and rd == od, (exp, t, rr, orr)
+        if t % 25 == 0 or t >= ec["GAME_STEPS"] - 1:
+            ro, rm = rs.observations(ref)
+            oo, om = orc.observe()
+            assert np.array_equal(ro, oo) and np.array_equal(bits(rm), bits(om)), (exp, t)
+    st = orc.state()
+    assert np.array_equal(rs.agent_metrics(ref), st["stats"])
+    assert np.array_equal(np.stack([ref.metrics["agent_visitation_maps"][i] for i in range(ce.N_AGENTS)]), st["visits"])
