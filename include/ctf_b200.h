@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CTF_ABI_VERSION 2
+#define CTF_ABI_VERSION 3
 
 #define CTF_MAX_AGENTS 8    /* largest AGENT_STARTING_POSITIONS in scenarios.py has 8 entries */
 #define CTF_MAX_GRID 16     /* GRID_SIZE <= 16 (shipped maps: 11, 13, 15) */
@@ -55,6 +55,12 @@ enum ctf_metric {
     CTF_M_STEPS_ADJ_TEAMMATE = 11,
     CTF_M_STEPS_ADJ_OPPONENT = 12
 };
+
+/* bits of the device fault word (ctf_take_faults) */
+#define CTF_FAULT_BAD_ACTION 1u      /* an action > 8 was passed (KeyError in ACTION_DELTAS, gridworld_ctf.py:710) */
+#define CTF_FAULT_RESPAWN_BLOCKED 2u /* a lethal tag found no open cell in the victim's 3x3 spawn window: the
+                                        reference raises ValueError from np.random.randint(0) (gridworld_ctf.py:771);
+                                        here the victim stays where it is with HP <= 0 and the bit is set */
 
 enum ctf_error {
     CTF_OK = 0,
@@ -214,7 +220,7 @@ int ctf_unpack_obs(ctf_handle_t h, const uint32_t* packed, void* out, int out_dt
  */
 int ctf_stats_sum(ctf_handle_t h, ctf_state_t state, int64_t* stats_sum, void* stream);
 
-/* Reads and clears the device fault word (bit 0: action out of range). Synchronises the stream. */
+/* Reads and clears the device fault word (CTF_FAULT_* bits). Synchronises the stream. */
 int ctf_take_faults(ctf_handle_t h, void* stream, uint32_t* faults);
 
 /*
@@ -226,6 +232,19 @@ int ctf_take_faults(ctf_handle_t h, void* stream, uint32_t* faults);
  */
 int ctf_step_host(ctf_handle_t h, ctf_state_t state, const uint8_t* actions_host, ctf_outputs_t out,
                   float* rewards_host, uint8_t* dones_host, void* stream);
+
+/*
+ * Which kernel ctf_step launches for this handle (no reference counterpart; for benchmarks and profiles).
+ * persistent = 1: the persistent warp-specialised kernel k_step_ws (ctas CTAs of logic_warps + stream_warps warps,
+ * envs handed out in order from a device counter); 0: the warp-per-env kernel k_step.  Both give identical results.
+ * One handle must not have two steps in flight on different streams (the persistent kernel's env counter and the
+ * host-step staging buffers are per handle).
+ */
+typedef struct ctf_kernel_info {
+    int persistent, logic_warps, stream_warps, ctas;
+    int64_t min_envs_for_persistent;
+} ctf_kernel_info_t;
+int ctf_get_kernel_info(ctf_handle_t h, ctf_kernel_info_t* out);
 
 #ifdef __cplusplus
 }

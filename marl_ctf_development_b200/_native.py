@@ -25,8 +25,10 @@ EXPORTS = (
     "ctf_stats_sum",
     "ctf_take_faults",
     "ctf_step_host",
+    "ctf_get_kernel_info",
 )
-ABI_VERSION = 2
+ABI_VERSION = 3
+FAULT_BAD_ACTION, FAULT_RESPAWN_BLOCKED = 1, 2
 
 
 class CtfState(C.Structure):
@@ -63,6 +65,11 @@ class CtfSizes(C.Structure):
             "bits_words_per_agent",
         )
     ]
+
+
+class CtfKernelInfo(C.Structure):
+    _fields_ = [("persistent", C.c_int), ("logic_warps", C.c_int), ("stream_warps", C.c_int), ("ctas", C.c_int),
+                ("min_envs_for_persistent", C.c_int64)]
 
 
 class NativeError(RuntimeError):
@@ -107,6 +114,7 @@ def load():
     L.ctf_unpack_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
     L.ctf_stats_sum.argtypes = [C.c_void_p, CtfState, C.c_void_p, C.c_void_p]
     L.ctf_take_faults.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+    L.ctf_get_kernel_info.argtypes = [C.c_void_p, C.POINTER(CtfKernelInfo)]
     L.ctf_step_host.argtypes = [C.c_void_p, CtfState, C.c_void_p, CtfOutputs, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.ctf_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI version mismatch: library {L.ctf_abi_version()}, binding {ABI_VERSION}")

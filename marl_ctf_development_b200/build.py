@@ -32,15 +32,37 @@ def is_stale() -> bool:
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compiles csrc/ctf_kernels.cu into libctf_b200.so next to this file. Returns the path."""
+    """Compiles csrc/ctf_kernels.cu into libctf_b200.so next to this file. Returns the path.
+
+    Safe when several ranks start at once (torchrun on a fresh checkout): one process at a time holds an flock,
+    nvcc writes to a temporary file and the finished library is moved into place atomically, so no rank can dlopen
+    a half-written file; the ranks that waited find an up-to-date library and do not compile again."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+    import fcntl
+    import tempfile
+
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():   # another rank built it while this one waited
+                return LIB
+            fd, tmp = tempfile.mkstemp(prefix=".libctf_b200.", suffix=".so.tmp", dir=_HERE)
+            os.close(fd)
+            try:
+                cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, SRC]
+                proc = subprocess.run(cmd, capture_output=True, text=True)
+                if proc.returncode != 0:
+                    raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+                os.chmod(tmp, 0o755)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+            if verbose:
+                print(proc.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>   // snprintf for error messages
+#include <stdlib.h>  // getenv: kernel-shape overrides for A/B runs
 #include <string.h>
 
 #include <new>
@@ -40,6 +41,11 @@ namespace {
 // evict_first policy) so that the 22 MB of state written by step t are still in L2 when step t+1 reads them.
 #define CTF_STATE_HINT 0
 #endif
+#ifndef CTF_DIAG
+// TIMING DIAGNOSTICS ONLY (results are wrong when non-zero): bit 0 skip the state read, 1 skip the state write-back,
+// 2 skip metadata, 3 skip rewards / dones, 4 skip the statistics reductions, 5 skip the actions read
+#define CTF_DIAG 0
+#endif
 constexpr int kWarpsPerCta = CTF_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kRow = 16;       // shared/global grid row stride (cells)
@@ -53,7 +59,7 @@ struct DevPlan {
     unsigned long long lut64[2];  // 4 bits per tile code -> channel, per observer team
     double reward_step, reward_capture, reward_tag, capture_punish, win_margin, loss_margin;
     int G, N, C, GG, M, E;        // E = N*C*G*G observation elements per env
-    int bits_words;               // words of the per-env observation bit string (incl. 1 pad word)
+    int bits_words;               // words of the per-env observation bit string (alignment pad + slack, multiple of 16)
     int wpa;                      // words per agent of the packed observation output: ceil(C*G*G / 32)
     int game_steps, flip_axis;
     int use_adjusted_rewards, home_flag_capture, drop_flag_when_no_hp, reverse_team1_actions;
@@ -263,7 +269,9 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 
 // Builds the env's observation block as one bit per element in shared memory (w.bits): element
 // e = (a*C + c)*G*G + p of the [N][C][G][G] block is bit e.
-__device__ __forceinline__ void build_obs_bits(const DevPlan& P, const WarpMem& w, uint32_t me, uint32_t rev_mask, int lane) {
+// `pad` (obs_pad of the output block) shifts the whole string: element e is bit pad + e, so that the store vectors,
+// counted from the alignment boundary below the block, cover whole nibbles / bytes / half-words of the string.
+__device__ __forceinline__ void build_obs_bits(const DevPlan& P, const WarpMem& w, uint32_t me, uint32_t rev_mask, int pad, int lane) {
     const int N = P.N, GG = P.GG, CGG = P.C * P.GG;
     // 1. clear the bit string
     {
@@ -294,7 +302,7 @@ __device__ __forceinline__ void build_obs_bits(const DevPlan& P, const WarpMem& 
         const bool valid = a < N;
         const bool rev = (rev_mask >> a) & 1u;
         const int ch_shift = P.team[a] ? 4 : 0, p_shift = rev ? 16 : 8;
-        const int base = a * CGG;
+        const int base = pad + a * CGG;
         for (int k = lane >> 3; k < count; k += 4) {
             const uint32_t ent = w.list[k];
             const int ch = (ent >> ch_shift) & 15;
@@ -312,48 +320,82 @@ __device__ __forceinline__ void build_obs_bits(const DevPlan& P, const WarpMem& 
     __syncwarp();
 }
 
-// Streams `nbits` elements (bit e of `bits` -> element e) to `out` with 128-bit stores; `bits` needs one readable
-// word past the last one.  Handles any alignment of `out` (scalar head/tail, funnel-shifted body).
+// elements (= bits of the string) per 128-bit store
 template <typename T>
-__device__ __forceinline__ void stream_bits(const uint32_t* bits, int nbits, T* __restrict__ out, int lane) {
-    constexpr int VEC = 16 / (int)sizeof(T);
-    const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(out) / sizeof(T)) % VEC);
-    const int head = mis ? min(VEC - (int)mis, nbits) : 0;
-    const int nvec = (nbits - head) / VEC;
-    const int tail = nbits - head - nvec * VEC;
-    if (lane < head) out[lane] = from_bit<T>((bits[lane >> 5] >> (lane & 31)) & 1u);
-    if (lane < tail) {
-        const int e = head + nvec * VEC + lane;
-        out[e] = from_bit<T>((bits[e >> 5] >> (e & 31)) & 1u);
-    }
-    uint4* __restrict__ vp = reinterpret_cast<uint4*>(out + head);
-    if (head == 0 && sizeof(T) == 4) {
-        // aligned float path: vector i is nibble (i & 7) of word (i >> 3)
-        const int sh = (lane & 7) * 4;
-        const uint32_t* wp = bits + (lane >> 3);
-        int i = lane;
-#pragma unroll 4
-        for (; i < nvec; i += 32, wp += 4) {
-            store_vec(vp + i, expand_bits<T>(*wp >> sh));
+constexpr int kVecElems = 16 / (int)sizeof(T);
+
+#ifndef CTF_PAD_BYTES
+// Alignment unit of the store vectors: 16 (vector), 32 (sector) or 128 (cache line).  Measured on one B200
+// (profiles/r02_ab_pad.log, ms per step 8_arena B=65536 / 7_gridlocked B=65536 / B=16384): 16 -> 1.003 / 0.618 / 0.173,
+// 32 -> 1.003 / 0.551 / 0.151, 128 -> 1.035 / 0.569 / 0.154: whole sectors matter (a sector shared by two store
+// instructions is written twice into L2), whole lines do not.
+#define CTF_PAD_BYTES 32
+#endif
+// number of elements between the previous CTF_PAD_BYTES boundary and `out`: 0 .. CTF_PAD_BYTES / sizeof(T) - 1
+template <typename T>
+__device__ __forceinline__ int obs_pad(const T* out) {
+    return (int)((reinterpret_cast<uintptr_t>(out) & (uintptr_t)(CTF_PAD_BYTES - 1)) / sizeof(T));
+}
+
+// Stores the full vectors [v_begin, v_end) of a padded bit string (vector v = bits VB*v .. VB*v + VB - 1) at vp[v];
+// warp `wi` of `nw` cooperating warps.  `bits` must be 16-byte aligned and readable up to a multiple of 16 words.
+template <typename T>
+__device__ __forceinline__ void stream_vectors(const uint32_t* __restrict__ bits, uint4* __restrict__ vp, int v_begin,
+                                               int v_end, int wi, int nw, int lane) {
+    if constexpr (sizeof(T) == 4) {
+        // group g = 128 vectors = 16 words = 2 KB of output: lane (q, n) = (lane >> 3, lane & 7) reads words
+        // 16g + 4q .. +3 with ONE 128-bit shared load and stores vector 8 * (16g + 4q + m) + n for m = 0..3, so every
+        // store instruction writes four complete 128-byte lines
+        const int q = lane >> 3, n = lane & 7, sh = n * 4;
+        const int n_groups = (v_end + 127) >> 7;
+#pragma unroll 2
+        for (int g = wi; g < n_groups; g += nw) {
+            const uint4 wd = *reinterpret_cast<const uint4*>(bits + 16 * g + 4 * q);
+            const int v0 = 128 * g + 32 * q + n;
+            if (v0 >= v_begin && v0 < v_end) store_vec(vp + v0, expand_bits<T>(wd.x >> sh));
+            if (v0 + 8 < v_end) store_vec(vp + v0 + 8, expand_bits<T>(wd.y >> sh));
+            if (v0 + 16 < v_end) store_vec(vp + v0 + 16, expand_bits<T>(wd.z >> sh));
+            if (v0 + 24 < v_end) store_vec(vp + v0 + 24, expand_bits<T>(wd.w >> sh));
         }
     } else {
-#pragma unroll 2
-        for (int i = lane; i < nvec; i += 32) {
-            const int o = head + i * VEC;
-            const uint32_t lo = bits[o >> 5], hi = bits[(o >> 5) + 1];
-            store_vec(vp + i, expand_bits<T>(__funnelshift_r(lo, hi, o & 31)));
-        }
+        constexpr int VB = kVecElems<T>, VW = 32 / VB;
+#pragma unroll 4
+        for (int v = wi * 32 + lane; v < v_end; v += nw * 32)
+            if (v >= v_begin) store_vec(vp + v, expand_bits<T>(bits[v / VW] >> ((v % VW) * VB)));
     }
+}
+
+// Streams `nbits` elements to `out` (any element alignment) from a bit string built with pad = obs_pad(out), i.e.
+// laid out from the CTF_PAD_BYTES boundary below `out`: store vectors are then sector-aligned whatever the block's
+// alignment (7_gridlocked's 52 728-byte env blocks start at every multiple of 8 bytes), no 32-byte sector is shared
+// by two store instructions.  Vectors that lie completely inside the block go out as 128-bit stores, the
+// fewer than VB elements before the first / after the last full vector as scalar stores (their neighbours belong
+// to other envs).
+template <typename T>
+__device__ __forceinline__ void stream_env(const uint32_t* __restrict__ bits, int nbits, T* __restrict__ out, int wi, int nw,
+                                           int lane) {
+    constexpr int VB = kVecElems<T>;
+    const int pad = obs_pad(out);
+    const int total = pad + nbits;
+    const int v_begin = (pad + VB - 1) / VB, v_end = total / VB;   // vectors counted from the alignment boundary
+    if (wi == 0) {
+        const int head_n = min(v_begin * VB - pad, nbits);          // < VB elements before the first full vector
+        if (lane < head_n) out[lane] = from_bit<T>((bits[(pad + lane) >> 5] >> ((pad + lane) & 31)) & 1u);
+        const int t = max(v_end * VB, pad + head_n) + lane;         // first bit covered by neither head nor full vectors
+        if (t < total) out[t - pad] = from_bit<T>((bits[t >> 5] >> (t & 31)) & 1u);
+    }
+    stream_vectors<T>(bits, reinterpret_cast<uint4*>(out - pad), v_begin, v_end, wi, nw, lane);
 }
 
 // Packed copy of the observation block for rollout storage: agent a's C*G*G bits start at word a*wpa
 // (32x smaller than float32; ctf_unpack_obs expands it again).
-__device__ __forceinline__ void store_packed(const DevPlan& P, const WarpMem& w, uint32_t* __restrict__ out_env, int lane) {
+__device__ __forceinline__ void store_packed(const DevPlan& P, const uint32_t* __restrict__ bits, int pad,
+                                             uint32_t* __restrict__ out_env, int wi, int nw, int lane) {
     const int CGG = P.C * P.GG, wpa = P.wpa, total = P.N * wpa;
-    for (int i = lane; i < total; i += 32) {
+    for (int i = wi * 32 + lane; i < total; i += nw * 32) {
         const int a = i / wpa, j = i - a * wpa;
-        const int o = a * CGG + 32 * j;
-        uint32_t v = __funnelshift_r(w.bits[o >> 5], w.bits[(o >> 5) + 1], o & 31);
+        const int o = pad + a * CGG + 32 * j;
+        uint32_t v = __funnelshift_r(bits[o >> 5], bits[(o >> 5) + 1], o & 31);
         const int valid = CGG - 32 * j;            // bits of this word that belong to agent a
         if (valid < 32) v &= (1u << valid) - 1u;
         out_env[i] = v;
@@ -364,9 +406,11 @@ template <typename T>
 __device__ __forceinline__ void write_obs(const DevPlan& P, const Launch& L, const WarpMem& w, long long env, uint32_t me,
                                           uint32_t rev_mask, int lane) {
     if (!L.obs && !L.obs_bits) return;
-    build_obs_bits(P, w, me, rev_mask, lane);
-    if (L.obs_bits) store_packed(P, w, L.obs_bits + env * (long long)(P.N * P.wpa), lane);
-    if (L.obs) stream_bits<T>(w.bits, P.E, reinterpret_cast<T*>(L.obs) + env * (long long)P.E, lane);
+    T* out = L.obs ? reinterpret_cast<T*>(L.obs) + env * (long long)P.E : nullptr;
+    const int pad = out ? obs_pad(out) : 0;
+    build_obs_bits(P, w, me, rev_mask, pad, lane);
+    if (L.obs_bits) store_packed(P, w.bits, pad, L.obs_bits + env * (long long)(P.N * P.wpa), 0, 1, lane);
+    if (out) stream_env<T>(w.bits, P.E, out, 0, 1, lane);
 }
 
 __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int step, int caps0, int caps1,
@@ -494,17 +538,23 @@ __global__ void __launch_bounds__(kThreads) k_observe(const __grid_constant__ De
 // ------------------------------------------------------------------------------------------------
 // step (gridworld_ctf.py:849-918) + observations for every agent
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool STATS>
-__global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L) {
-    extern __shared__ uint4 smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long env = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (env >= L.B) return;
-    const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw), warp);
+// One env step by one warp: state in, act / tag / respawn / heal / rewards / statistics / metadata, state out.
+// Returns the lane's agent register (position for the observation's self plane) and the per-agent reverse_grid mask;
+// the tile map of the new state is left in w.grid for the observation writer.
+template <bool STATS>
+__device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, const WarpMem& w, long long env, int lane,
+                                             uint32_t& rev_mask_out) {
     const int N = P.N;
     const int li = lane & 7;
 
     // ---- stage state: tile map -> shared memory, agent i -> lane i
+#if CTF_DIAG & 1
+    if (lane < kGridBytes / 16) reinterpret_cast<uint4*>(w.grid)[lane] = reinterpret_cast<const uint4*>(P.grid_template)[lane];
+    uint32_t me = pack_agent(P.start_r[lane & 7], P.start_c[lane & 7], 0, P.hp_max_q[P.type[lane & 7]]);
+    int inv = 0;
+    int action = (CTF_DIAG & 32) ? (int)((env + lane) % 9) : (lane < N ? L.actions[env * N + lane] : 4);
+    uint4 ev = make_uint4((uint32_t)(env & 255), 0, 0, 0);
+#else
     if (lane < kGridBytes / 16)
         reinterpret_cast<uint4*>(w.grid)[lane] = ld_state(reinterpret_cast<const uint4*>(L.grid + env * kGridBytes) + lane);
     uint32_t me = 0;
@@ -514,14 +564,15 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
         const unsigned long long rec = ld_state(L.agents + env * N + lane);
         me = pack_agent((int)(rec & 0xFF), (int)((rec >> 8) & 0xFF), (int)((rec >> 16) & 1), (int)(short)(rec >> 32));
         inv = (int)((rec >> 48) & 0xFFFF);
-        action = L.actions[env * N + lane];
+        action = (CTF_DIAG & 32) ? (int)((env + lane) % 9) : L.actions[env * N + lane];
     }
     uint4 ev = ld_state(L.envs + env);
+#endif
     Deltas dl;
     const int my_team = P.team[li], my_type = P.type[li], my_slot = P.my_slot[li];
     const bool bad_action = lane < N && action >= CTF_N_ACTIONS;
     if (__any_sync(kFull, bad_action)) {
-        if (lane == 0) atomicOr(L.faults, 1u);
+        if (lane == 0) atomicOr(L.faults, CTF_FAULT_BAD_ACTION);
         if (bad_action) action = 4;
     }
     if (P.reverse_team1_actions && my_team == 1) action = P.rev_action[action];
@@ -665,6 +716,8 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
                     }
                     __syncwarp();
                     if (lane == opp) me = pack_agent(rr, rc, 0, P.hp_max_q[P.type[opp]]);
+                } else if (lane == 0) {
+                    atomicOr(L.faults, CTF_FAULT_RESPAWN_BLOCKED);   // randint(0) raises in the reference (:771)
                 }
                 if (lane == a) tag_reward = true;
                 bump<STATS>(dl, CTF_M_RESPAWN_TAG_COUNT, a, 1, lane);
@@ -708,22 +761,28 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
             if (my_team == winner) r = __dadd_rn(r, __dmul_rn(margin, P.win_margin));
             else r = __dadd_rn(r, -__dmul_rn(margin, P.loss_margin));
         }
-        if (L.rewards && lane < N) L.rewards[env * N + lane] = (float)r;
+        if (!(CTF_DIAG & 8) && L.rewards && lane < N) L.rewards[env * N + lane] = (float)r;
     }
-    if (L.dones && lane == 0) L.dones[env] = done ? 1 : 0;
+    if (!(CTF_DIAG & 8) && L.dones && lane == 0) L.dones[env] = done ? 1 : 0;
     ev.z = (uint32_t)caps0;
     ev.w = (uint32_t)caps1;
 
     // ---- write state back
     __syncwarp();
-    store_state(P, L, w, env, me, inv, ev, lane);
-    if (STATS) {
+    if (!(CTF_DIAG & 2)) store_state(P, L, w, env, me, inv, ev, lane);
+    if (STATS && !(CTF_DIAG & 16)) {
         if (lane < N) {   // fire-and-forget reductions: no load latency, nothing held in registers
             uint32_t* sp = L.stats + env * (long long)(CTF_N_METRICS * N) + lane;
 #pragma unroll
             for (int m = 0; m < CTF_N_METRICS; ++m) {
                 const uint32_t v = ((m < 8 ? dl.lo : dl.hi) >> (4 * (m & 7))) & 15u;
-                if (v) atomicAdd(sp + m * N, v);
+                if (v) {
+#if CTF_STATE_HINT
+                    asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(sp + m * N), "r"(v), "l"(l2_evict_last()) : "memory");
+#else
+                    atomicAdd(sp + m * N, v);
+#endif
+                }
             }
         }
         if (L.visits && lane < N) {   // update_visitation_map (:911), uint8 wrap
@@ -732,28 +791,195 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
         }
     }
 
-    // ---- observations straight into the policy's input buffers
-    const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
-                                                        : __ballot_sync(kFull, lane < N && P.obs_rev[li]);
-    if (L.meta) write_meta(P, me, step, caps0, caps1, L.meta + env * (long long)N * P.M, lane);
-    write_obs<T>(P, L, w, env, me, rev_mask, lane);
+    rev_mask_out = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu) : __ballot_sync(kFull, lane < N && P.obs_rev[li]);
+    if (!(CTF_DIAG & 4) && L.meta) write_meta(P, me, step, caps0, caps1, L.meta + env * (long long)N * P.M, lane);
+    return me;
+}
+
+// Warp-per-env step kernel: every warp steps its env and then streams that env's observation block itself.
+// Used for small batches (under a few waves of the persistent kernel below) and as the A/B baseline.
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long env = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (env >= L.B) return;
+    const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw), warp);
+    uint32_t rev_mask;
+    const uint32_t me = step_env<STATS>(P, L, w, env, lane, rev_mask);
+    write_obs<T>(P, L, w, env, me, rev_mask, lane);   // observations straight into the policy's input buffers
 }
 
 // ------------------------------------------------------------------------------------------------
-// packed observations -> policy input: one warp per agent block (wpa words -> C*G*G elements)
+// Persistent, warp-specialised step kernel (the hot kernel at large B)
 // ------------------------------------------------------------------------------------------------
-constexpr int kUnpackWarps = 8;
-template <typename T>
-__global__ void __launch_bounds__(kUnpackWarps * 32) k_unpack(const uint32_t* __restrict__ packed, T* __restrict__ out,
-                                                             long long n_blocks, int nbits, int wpa) {
+// What bounds the step is the 100 KB-per-env observation write, and HBM takes that stream fastest when few env
+// blocks are open at a time and they are visited in address order (profiles/r02_write_span_microbench.log: 0.88 ms
+// for 65536 blocks written one per 512-thread CTA in order, 0.96 ms when every warp streams its own block).  SMs
+// also differ by up to 1.46x in store bandwidth, so work has to be handed out dynamically.  Hence:
+//   * one persistent CTA per SM (or two): n_logic "logic" warps + n_stream "stream" warps;
+//   * a logic warp takes the next env id from a global counter (in order), runs step_env, builds the env's
+//     observation bit string in its own shared-memory buffer and queues it in a shared-memory FIFO;
+//   * the stream warps take the FIFO entries in order and write ONE env block at a time, together;
+//   * a logic warp reuses its buffer when the stream group is done with it — the queue is the back-pressure.
+#ifndef CTF_WS_PROFILE
+#define CTF_WS_PROFILE 0         // 1: per-phase cycle totals of logic / stream warps (tools/ws_sweep.py --profile build)
+#endif
+#if CTF_WS_PROFILE
+#define CTF_PROF_T(var) const long long var = clock64()
+#define CTF_PROF_ADD(acc, t0, t1) acc += (t1) - (t0)
+#else
+#define CTF_PROF_T(var)
+#define CTF_PROF_ADD(acc, t0, t1)
+#endif
+constexpr int kWsQ = 32;         // FIFO slots (>= logic warps per CTA)
+constexpr int kWsCtlBytes = 1024;
+struct WsCtl {
+    int tail;                    // next ticket
+    int producers;               // logic warps still running
+    volatile int ready[kWsQ];    // ticket + 1 once the entry is filled, 0 when free
+    int env[kWsQ];
+    int buf[kWsQ];               // logic warp whose buffer holds the bit string
+    int done[kWsQ];              // stream warps finished with the entry
+    volatile int busy[32];       // logic warp's buffer is queued / being streamed
+};
+static_assert(sizeof(WsCtl) <= kWsCtlBytes, "control block");
+
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L,
+                                                     int n_logic, int n_stream, unsigned int* __restrict__ ctr) {
     extern __shared__ uint4 smem_raw[];
+    WsCtl* c = reinterpret_cast<WsCtl*>(smem_raw);
+    unsigned char* warp_base = reinterpret_cast<unsigned char*>(smem_raw) + kWsCtlBytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long blk = (long long)blockIdx.x * kUnpackWarps + warp;
-    if (blk >= n_blocks) return;
-    uint32_t* bits = reinterpret_cast<uint32_t*>(smem_raw) + warp * (wpa + 4);
-    for (int i = lane; i < wpa + 1; i += 32) bits[i] = i < wpa ? __ldg(packed + blk * wpa + i) : 0u;
-    __syncwarp();
-    stream_bits<T>(bits, nbits, out + blk * (long long)nbits, lane);
+    if (threadIdx.x == 0) { c->tail = 0; c->producers = n_logic; }
+    if (threadIdx.x < kWsQ) { c->ready[threadIdx.x] = 0; c->done[threadIdx.x] = 0; }
+    if (threadIdx.x < 32) c->busy[threadIdx.x] = 0;
+    __syncthreads();
+    const bool any_obs = L.obs || L.obs_bits;
+#if CTF_WS_PROFILE
+    long long pf[6] = {0, 0, 0, 0, 0, 0};   // logic: fetch, step, wait, build+publish; stream: idle, stream
+    unsigned long long* prof = reinterpret_cast<unsigned long long*>(ctr + 4);
+#endif
+    if (warp < n_logic) {
+        const WarpMem w = warp_mem(P, warp_base, warp);
+        for (;;) {
+            CTF_PROF_T(t0);
+            unsigned int e = 0;
+            if (lane == 0) e = atomicAdd(ctr, 1u);
+            e = __shfl_sync(kFull, e, 0);
+            if ((long long)e >= L.B) break;
+            CTF_PROF_T(t1);
+            uint32_t rev_mask;
+            const uint32_t me = step_env<STATS>(P, L, w, (long long)e, lane, rev_mask);
+            if (!any_obs) continue;
+            CTF_PROF_T(t2);
+            if (lane == 0) while (c->busy[warp]) __nanosleep(32);   // previous env of this warp still being streamed
+            __syncwarp();
+            CTF_PROF_T(t3);
+            const int pad = L.obs ? obs_pad(reinterpret_cast<T*>(L.obs) + (long long)e * P.E) : 0;
+            build_obs_bits(P, w, me, rev_mask, pad, lane);
+            if (lane == 0) {
+                c->busy[warp] = 1;
+                const int t = atomicAdd(&c->tail, 1);
+                const int slot = t % kWsQ;
+                while (c->ready[slot] != 0) __nanosleep(32);
+                c->env[slot] = (int)e;
+                c->buf[slot] = warp;
+                __threadfence_block();
+                c->ready[slot] = t + 1;
+            }
+            __syncwarp();
+            CTF_PROF_T(t4);
+            CTF_PROF_ADD(pf[0], t0, t1); CTF_PROF_ADD(pf[1], t1, t2); CTF_PROF_ADD(pf[2], t2, t3); CTF_PROF_ADD(pf[3], t3, t4);
+        }
+        if (lane == 0) {
+#if CTF_WS_PROFILE
+            for (int i = 0; i < 4; ++i) atomicAdd(prof + i, (unsigned long long)pf[i]);
+#endif
+            atomicSub(&c->producers, 1);
+            // every logic warp of the grid fails its last fetch exactly once; the last one re-arms the counters
+            if (atomicAdd(ctr + 1, 1u) == gridDim.x * (unsigned)n_logic - 1u) { ctr[0] = 0; ctr[1] = 0; }
+        }
+    } else {
+        const int wi = warp - n_logic;
+        for (int head = 0;; ++head) {
+            const int slot = head % kWsQ;
+            int got = 0;
+            CTF_PROF_T(t0);
+            if (lane == 0) {
+                for (;;) {
+                    if (c->ready[slot] == head + 1) { got = 1; break; }
+                    if (*(volatile int*)&c->producers == 0 && *(volatile int*)&c->tail == head) break;
+                    __nanosleep(32);
+                }
+                __threadfence_block();
+            }
+            got = __shfl_sync(kFull, got, 0);
+            if (!got) break;
+            CTF_PROF_T(t1);
+            const long long env = c->env[slot];
+            const int buf = c->buf[slot];
+            const uint32_t* bits = warp_mem(P, warp_base, buf).bits;
+            T* out = L.obs ? reinterpret_cast<T*>(L.obs) + env * (long long)P.E : nullptr;
+            if (L.obs_bits) store_packed(P, bits, out ? obs_pad(out) : 0, L.obs_bits + env * (long long)(P.N * P.wpa), wi, n_stream, lane);
+            if (out) stream_env<T>(bits, P.E, out, wi, n_stream, lane);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&c->done[slot], 1) == n_stream - 1) {   // last stream warp frees the buffer and the slot
+                    c->done[slot] = 0;
+                    c->busy[buf] = 0;
+                    __threadfence_block();
+                    c->ready[slot] = 0;
+                }
+            }
+            CTF_PROF_T(t2);
+            CTF_PROF_ADD(pf[4], t0, t1); CTF_PROF_ADD(pf[5], t1, t2);
+        }
+#if CTF_WS_PROFILE
+        if (lane == 0) { atomicAdd(prof + 4, (unsigned long long)pf[4]); atomicAdd(prof + 5, (unsigned long long)pf[5]); }
+#endif
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed observations -> policy input: one CTA per chunk of consecutive agent blocks
+// ------------------------------------------------------------------------------------------------
+// The chunk's packed words (wpa per block, coalesced) are re-packed in shared memory into ONE contiguous bit string
+// (block b's nbits elements follow block b-1's directly, shifted by the output's alignment pad) and all warps stream
+// the chunk's output region together — CTAs are scheduled in address order, so few blocks are open at a time.
+constexpr int kUnpackThreads = 256;
+template <typename T>
+__global__ void __launch_bounds__(kUnpackThreads) k_unpack(const uint32_t* __restrict__ packed, T* __restrict__ out,
+                                                          long long n_blocks, int nbits, int wpa, int chunk, int bits_words) {
+    extern __shared__ uint4 smem_raw[];
+    uint32_t* bits = reinterpret_cast<uint32_t*>(smem_raw);   // [bits_words]
+    uint32_t* pk = bits + bits_words;                          // [chunk * wpa]
+    const long long blk0 = (long long)blockIdx.x * chunk;
+    const int nb = (int)min((long long)chunk, n_blocks - blk0);
+    if (nb <= 0) return;
+    for (int i = threadIdx.x; i < nb * wpa; i += kUnpackThreads) pk[i] = __ldg(packed + blk0 * wpa + i);
+    __syncthreads();
+    T* dst = out + blk0 * (long long)nbits;
+    const int pad = obs_pad(dst), total = nb * nbits;
+    for (int wd = threadIdx.x; wd < bits_words; wd += kUnpackThreads) {
+        uint32_t val = 0;
+        int k = 0, e = 32 * wd - pad;              // bit k of this word is element e + k of the chunk
+        if (e < 0) { k = -e; e = 0; }
+        while (k < 32 && e < total) {
+            const int b = e / nbits, o = e - b * nbits, j = o >> 5;
+            const int take = min(32 - k, nbits - o);
+            const uint32_t lo = pk[b * wpa + j], hi = j + 1 < wpa ? pk[b * wpa + j + 1] : 0u;
+            uint32_t v = __funnelshift_r(lo, hi, o & 31);
+            if (take < 32) v &= (1u << take) - 1u;
+            val |= v << k;
+            k += take; e += take;
+        }
+        bits[wd] = val;
+    }
+    __syncthreads();
+    stream_env<T>(bits, total, dst, threadIdx.x >> 5, kUnpackThreads / 32, threadIdx.x & 31);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -790,7 +1016,29 @@ struct ctf_env {
     float* rewards_stage;    // device [B][N], used by ctf_step_host when out.rewards is NULL
     uint8_t* dones_stage;    // device [B]
     size_t smem_bytes;
+    // persistent warp-specialised step kernel (k_step_ws)
+    unsigned int* ws_ctr;    // device [2]: next env id, logic warps that have finished; re-armed by the kernel itself
+    int ws_logic, ws_stream, ws_ctas;   // logic / stream warps per CTA, CTAs in the grid
+    long long ws_min_envs;   // batches below this use the warp-per-env kernel
+    size_t ws_smem_bytes;
 };
+
+// cudaSetDevice for the duration of an entry point; the caller's current device is restored on return
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : fallback;
+}
 
 static thread_local char g_err[512] = "";
 
@@ -822,7 +1070,7 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
     P.reward_step = c.reward_step; P.reward_capture = c.reward_capture; P.reward_tag = c.reward_tag;
     P.capture_punish = c.capture_punish; P.win_margin = c.win_margin_scalar; P.loss_margin = c.loss_margin_scalar;
     P.G = G; P.N = N; P.C = c.n_channels; P.GG = G * G; P.M = 6 + 2 * N; P.E = N * c.n_channels * G * G;
-    P.bits_words = (P.E + 31) / 32 + 1;
+    P.bits_words = (((P.E + 128 + 31) / 32 + 1) + 15) / 16 * 16;  // pad (<= 127 bits) + 1 slack word, whole 16-word groups
     P.wpa = (c.n_channels * G * G + 31) / 32;
     P.game_steps = c.game_steps; P.flip_axis = c.flip_axis;
     P.use_adjusted_rewards = c.use_adjusted_rewards; P.home_flag_capture = c.home_flag_capture;
@@ -919,23 +1167,52 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
     h->seed = seed; h->env_id_base = env_id_base;
     h->smem_bytes = (size_t)h->plan.warp_smem_bytes * kWarpsPerCta;
     h->faults = nullptr; h->actions_stage = nullptr; h->rewards_stage = nullptr; h->dones_stage = nullptr;
-    cudaError_t e = cudaSetDevice(device);
+    DeviceGuard guard(device);
+    cudaError_t e = guard.err;
     if (e == cudaSuccess) e = cudaMalloc(&h->faults, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(h->faults, 0, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&h->actions_stage, (size_t)num_envs * cfg->n_agents);
     if (e == cudaSuccess) e = cudaMalloc(&h->rewards_stage, (size_t)num_envs * cfg->n_agents * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&h->dones_stage, (size_t)num_envs);
+    h->ws_ctr = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&h->ws_ctr, 128);   // two 32-bit counters (+ the profiling build's cycle totals)
+    if (e == cudaSuccess) e = cudaMemset(h->ws_ctr, 0, 128);
+    // Shape of the persistent kernel: one CTA per SM with 8 logic + 12 stream warps unless overridden (A/B runs,
+    // tools/ws_sweep.py).  It beats the warp-per-env kernel only where the observation stream dwarfs the env logic —
+    // float32 8_arena-sized blocks (>= 12 KB per agent): 0.989 vs 1.003 ms at B = 65536, 0.264 vs 0.269 ms at 16384 —
+    // and loses where the logic is a larger share (7_gridlocked 0.73 vs 0.55 ms, uint8 / bf16 / packed-only outputs):
+    // profiles/r02_ws_matrix.log, r02_ab_pad.log.  CTF_WS=1 / 0 forces it on / off.
+    int n_sm = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    h->ws_logic = env_int("CTF_WS_LOGIC", 8);
+    h->ws_stream = env_int("CTF_WS_STREAM", 12);
+    const int ctas_per_sm = env_int("CTF_WS_CTAS_PER_SM", 1);
+    if (h->ws_logic < 1 || h->ws_logic > kWsQ || h->ws_stream < 1 || (h->ws_logic + h->ws_stream) > 32 || ctas_per_sm < 1 ||
+        ctas_per_sm > 4) {
+        cudaFree(h->faults); cudaFree(h->actions_stage); cudaFree(h->rewards_stage); cudaFree(h->dones_stage); cudaFree(h->ws_ctr);
+        delete h;
+        return fail(CTF_ERR_INVALID, "CTF_WS_LOGIC / CTF_WS_STREAM / CTF_WS_CTAS_PER_SM out of range");
+    }
+    h->ws_ctas = n_sm * ctas_per_sm;
+    h->ws_smem_bytes = (size_t)kWsCtlBytes + (size_t)h->plan.warp_smem_bytes * h->ws_logic;
+    // below ~4 envs per logic warp the persistent kernel is all ramp-up and tail: use the warp-per-env kernel
+    h->ws_min_envs = (long long)env_int("CTF_WS_MIN_ENVS", 4 * h->ws_ctas * h->ws_logic);
+    const size_t obs_bytes_per_agent = (size_t)h->plan.C * h->plan.GG * (obs_dtype == CTF_OBS_F32 ? 4 : (obs_dtype == CTF_OBS_U8 ? 1 : 2));
+    const int ws_mode = env_int("CTF_WS", -1);   // -1: by the heuristic above
+    if (ws_mode == 0 || (ws_mode < 0 && obs_bytes_per_agent < 12000) || num_envs > 0x7FFFFFFFll) h->ws_min_envs = 0x7FFFFFFFFFFFFFFFll;
     const int smem = (int)h->smem_bytes;
-#define CTF_SET_SMEM(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-#define CTF_SET_SMEM_T(T)                                                                                    \
-    CTF_SET_SMEM((k_step<T, false>)); CTF_SET_SMEM((k_step<T, true>)); CTF_SET_SMEM((k_reset<T, false>)); \
-    CTF_SET_SMEM((k_reset<T, true>)); CTF_SET_SMEM((k_observe<T>))
+    const int ws_smem = (int)h->ws_smem_bytes;
+#define CTF_SET_SMEM(K, BYTES) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)
+#define CTF_SET_SMEM_T(T)                                                                                       \
+    CTF_SET_SMEM((k_step<T, false>), smem); CTF_SET_SMEM((k_step<T, true>), smem);                             \
+    CTF_SET_SMEM((k_reset<T, false>), smem); CTF_SET_SMEM((k_reset<T, true>), smem); CTF_SET_SMEM((k_observe<T>), smem); \
+    CTF_SET_SMEM((k_step_ws<T, false>), ws_smem); CTF_SET_SMEM((k_step_ws<T, true>), ws_smem)
     CTF_SET_SMEM_T(float); CTF_SET_SMEM_T(uint8_t); CTF_SET_SMEM_T(__half); CTF_SET_SMEM_T(__nv_bfloat16);
 #undef CTF_SET_SMEM_T
 #undef CTF_SET_SMEM
     if (e != cudaSuccess) {
         fail(CTF_ERR_CUDA, "ctf_create: %s", cudaGetErrorString(e));
-        cudaFree(h->faults); cudaFree(h->actions_stage); cudaFree(h->rewards_stage); cudaFree(h->dones_stage);
+        cudaFree(h->faults); cudaFree(h->actions_stage); cudaFree(h->rewards_stage); cudaFree(h->dones_stage); cudaFree(h->ws_ctr);
         delete h;
         return CTF_ERR_CUDA;
     }
@@ -945,8 +1222,8 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
 
 extern "C" int ctf_destroy(ctf_handle_t h) {
     if (!h) return CTF_OK;
-    cudaSetDevice(h->device);
-    cudaFree(h->faults); cudaFree(h->actions_stage); cudaFree(h->rewards_stage); cudaFree(h->dones_stage);
+    DeviceGuard guard(h->device);
+    cudaFree(h->faults); cudaFree(h->actions_stage); cudaFree(h->rewards_stage); cudaFree(h->dones_stage); cudaFree(h->ws_ctr);
     delete h;
     return CTF_OK;
 }
@@ -1010,7 +1287,8 @@ extern "C" int ctf_reset(ctf_handle_t h, ctf_state_t st, ctf_outputs_t out, int 
     int rc = make_launch(h, st, out, L);
     if (rc != CTF_OK) return rc;
     L.first_reset = first ? 1 : 0;
-    CTF_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    CTF_CUDA(guard.err);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool stats = h->stats_level > 0;
     with_obs_type(h->obs_dtype, [&](auto tag) {
@@ -1024,10 +1302,17 @@ extern "C" int ctf_reset(ctf_handle_t h, ctf_state_t st, ctf_outputs_t out, int 
 
 static int launch_step(ctf_handle_t h, const Launch& L, cudaStream_t s) {
     const bool stats = h->stats_level > 0;
+    const bool ws = h->B >= h->ws_min_envs;
     with_obs_type(h->obs_dtype, [&](auto tag) {
         using T = decltype(tag);
-        if (stats) k_step<T, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-        else k_step<T, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+        if (ws) {
+            const unsigned threads = (unsigned)(h->ws_logic + h->ws_stream) * 32u;
+            if (stats) k_step_ws<T, true><<<h->ws_ctas, threads, h->ws_smem_bytes, s>>>(h->plan, L, h->ws_logic, h->ws_stream, h->ws_ctr);
+            else k_step_ws<T, false><<<h->ws_ctas, threads, h->ws_smem_bytes, s>>>(h->plan, L, h->ws_logic, h->ws_stream, h->ws_ctr);
+        } else {
+            if (stats) k_step<T, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+            else k_step<T, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+        }
     });
     CTF_CUDA(cudaGetLastError());
     return CTF_OK;
@@ -1040,7 +1325,8 @@ extern "C" int ctf_step(ctf_handle_t h, ctf_state_t st, const uint8_t* actions, 
     int rc = make_launch(h, st, out, L);
     if (rc != CTF_OK) return rc;
     L.actions = actions;
-    CTF_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    CTF_CUDA(guard.err);
     return launch_step(h, L, static_cast<cudaStream_t>(stream));
 }
 
@@ -1054,7 +1340,8 @@ extern "C" int ctf_observe(ctf_handle_t h, ctf_state_t st, const uint8_t* revers
         for (int i = 0; i < h->plan.N; ++i) m |= (reverse_flags[i] ? 1u : 0u) << i;
         L.rev_override = m;
     }
-    CTF_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    CTF_CUDA(guard.err);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     with_obs_type(h->obs_dtype, [&](auto tag) {
         k_observe<decltype(tag)><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
@@ -1069,14 +1356,19 @@ extern "C" int ctf_unpack_obs(ctf_handle_t h, const uint32_t* packed, void* out,
     if (out_dtype < CTF_OBS_F32 || out_dtype > CTF_OBS_BF16) return fail(CTF_ERR_INVALID, "unknown obs dtype");
     if (n_agent_blocks < 0) return fail(CTF_ERR_INVALID, "negative block count");
     if (n_agent_blocks == 0) return CTF_OK;
-    CTF_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    CTF_CUDA(guard.err);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int nbits = h->plan.C * h->plan.GG, wpa = h->plan.wpa;
-    const unsigned grid = (unsigned)((n_agent_blocks + kUnpackWarps - 1) / kUnpackWarps);
-    const size_t smem = (size_t)kUnpackWarps * (wpa + 4) * sizeof(uint32_t);
+    const int elem = out_dtype == CTF_OBS_F32 ? 4 : (out_dtype == CTF_OBS_U8 ? 1 : 2);
+    int chunk = (96 * 1024) / (nbits * elem);          // ~96 KB of output per CTA
+    chunk = chunk < 1 ? 1 : (chunk > 64 ? 64 : chunk);
+    const int bits_words = (((chunk * nbits + 128 + 31) / 32 + 1) + 15) / 16 * 16;
+    const unsigned grid = (unsigned)((n_agent_blocks + chunk - 1) / chunk);
+    const size_t smem = ((size_t)bits_words + (size_t)chunk * wpa) * sizeof(uint32_t);
     with_obs_type(out_dtype, [&](auto tag) {
         using T = decltype(tag);
-        k_unpack<T><<<grid, kUnpackWarps * 32, smem, s>>>(packed, static_cast<T*>(out), n_agent_blocks, nbits, wpa);
+        k_unpack<T><<<grid, kUnpackThreads, smem, s>>>(packed, static_cast<T*>(out), n_agent_blocks, nbits, wpa, chunk, bits_words);
     });
     CTF_CUDA(cudaGetLastError());
     return CTF_OK;
@@ -1085,7 +1377,8 @@ extern "C" int ctf_unpack_obs(ctf_handle_t h, const uint32_t* packed, void* out,
 extern "C" int ctf_stats_sum(ctf_handle_t h, ctf_state_t st, int64_t* stats_sum, void* stream) {
     if (!h || !stats_sum) return fail(CTF_ERR_INVALID, "null argument");
     if (h->stats_level == 0 || !st.stats) return fail(CTF_ERR_INVALID, "handle was created without statistics");
-    CTF_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    CTF_CUDA(guard.err);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int ns = CTF_N_METRICS * h->plan.N;
     CTF_CUDA(cudaMemsetAsync(stats_sum, 0, sizeof(int64_t) * ns, s));
@@ -1096,9 +1389,18 @@ extern "C" int ctf_stats_sum(ctf_handle_t h, ctf_state_t st, int64_t* stats_sum,
     return CTF_OK;
 }
 
+extern "C" int ctf_get_kernel_info(ctf_handle_t h, ctf_kernel_info_t* out) {
+    if (!h || !out) return fail(CTF_ERR_INVALID, "null argument");
+    out->persistent = h->B >= h->ws_min_envs ? 1 : 0;
+    out->logic_warps = h->ws_logic; out->stream_warps = h->ws_stream; out->ctas = h->ws_ctas;
+    out->min_envs_for_persistent = h->ws_min_envs;
+    return CTF_OK;
+}
+
 extern "C" int ctf_take_faults(ctf_handle_t h, void* stream, uint32_t* faults) {
     if (!h || !faults) return fail(CTF_ERR_INVALID, "null argument");
-    CTF_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    CTF_CUDA(guard.err);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CTF_CUDA(cudaMemcpyAsync(faults, h->faults, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CTF_CUDA(cudaMemsetAsync(h->faults, 0, sizeof(uint32_t), s));
@@ -1118,7 +1420,8 @@ extern "C" int ctf_step_host(ctf_handle_t h, ctf_state_t st, const uint8_t* acti
                              float* rewards_host, uint8_t* dones_host, void* stream) {
     if (!h) return fail(CTF_ERR_INVALID, "null handle");
     if (!actions_host) return fail(CTF_ERR_INVALID, "actions_host must not be null");
-    CTF_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    CTF_CUDA(guard.err);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)h->B * h->plan.N;
     // Pinned host buffers are read / written by the kernel itself over PCIe (zero-copy): 8 B of actions in and
@@ -1148,3 +1451,14 @@ extern "C" int ctf_step_host(ctf_handle_t h, ctf_state_t st, const uint8_t* acti
     CTF_CUDA(cudaStreamSynchronize(s));
     return CTF_OK;
 }
+
+#if CTF_WS_PROFILE
+// profiling builds only (tools/ws_sweep.py --profile): cycle totals {fetch, step, wait, build, stream-idle, stream}, then cleared
+extern "C" int ctf_debug_ws_profile(ctf_handle_t h, unsigned long long* out6) {
+    DeviceGuard guard(h->device);
+    CTF_CUDA(cudaDeviceSynchronize());
+    CTF_CUDA(cudaMemcpy(out6, reinterpret_cast<unsigned char*>(h->ws_ctr) + 16, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CTF_CUDA(cudaMemset(reinterpret_cast<unsigned char*>(h->ws_ctr) + 16, 0, 6 * sizeof(unsigned long long)));
+    return CTF_OK;
+}
+#endif

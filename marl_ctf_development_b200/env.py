@@ -259,14 +259,18 @@ class GridworldCtfGPU:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self.step(a)
+            self.step(a)   # with validate_actions this also checks the actions once, outside the capture
             for t, s_ in zip(state, saved):
                 t.copy_(s_)
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for _ in range(int(steps_per_replay)):
-                self.step(a)
+        validate, self.validate_actions = self.validate_actions, False   # ctf_take_faults synchronises: not capturable
+        try:
+            with torch.cuda.graph(graph):
+                for _ in range(int(steps_per_replay)):
+                    self.step(a)
+        finally:
+            self.validate_actions = validate
         return graph
 
     def step_host(self, actions_host: torch.Tensor, rewards_host: torch.Tensor, dones_host: torch.Tensor):
@@ -332,11 +336,30 @@ class GridworldCtfGPU:
             actions = torch.where((actions < 0) | (actions > 8), torch.full_like(actions, 255), actions).to(torch.uint8)
         return actions.to(self.device, non_blocking=True).contiguous()
 
-    def raise_on_faults(self):
+    def take_faults(self) -> int:
+        """Reads and clears the device fault word (synchronises): bit 0 = action outside 0..8, bit 1 = a lethal tag
+        found the victim's 3x3 spawn window full (the reference raises there, gridworld_ctf.py:771)."""
         f = C.c_uint32(0)
         _native.check(self._lib.ctf_take_faults(self._handle, self._stream(), C.byref(f)))
-        if f.value & 1:
+        return int(f.value)
+
+    def raise_on_faults(self):
+        f = self.take_faults()
+        if f & _native.FAULT_BAD_ACTION:
             raise KeyError("an action outside 0..8 was passed to step() (KeyError in the reference's ACTION_DELTAS lookup)")
+        if f & _native.FAULT_RESPAWN_BLOCKED:
+            raise ValueError("respawn found no open cell in a 3x3 spawn window (np.random.randint(0) raises ValueError in "
+                             "the reference, gridworld_ctf.py:771); the victim was left in place with HP <= 0")
+
+    @property
+    def uses_persistent_kernel(self) -> bool:
+        """True when step() launches the persistent warp-specialised kernel for this batch size (see ctf_get_kernel_info)."""
+        return bool(self.kernel_info().persistent)
+
+    def kernel_info(self):
+        info = _native.CtfKernelInfo()
+        _native.check(self._lib.ctf_get_kernel_info(self._handle, C.byref(info)))
+        return info
 
     # ------------------------------------------------------------------ reference API that does not touch the device
     def get_env_dims(self):
@@ -350,13 +373,24 @@ class GridworldCtfGPU:
         return torch.tensor([self.get_reversed_action(a) for a in range(9)], dtype=torch.int64, device=self.device)
 
     # ------------------------------------------------------------------ state access (tests, snapshots)
-    def get_state(self) -> dict:
-        """Decoded device state as CPU numpy arrays (synchronises)."""
+    def get_state(self, env_index=None) -> dict:
+        """Decoded device state as CPU numpy arrays (synchronises).  ``env_index`` (int or slice) copies only those
+        envs off the device; every array keeps its leading env axis."""
         G = self.GRID_SIZE
-        rec = self._agents.cpu().numpy().astype(np.uint64)
-        envs = self._envs.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        if env_index is None:
+            sel = slice(None)
+        elif isinstance(env_index, slice):
+            sel = env_index
+        else:
+            i = int(env_index)
+            if not -self.num_envs <= i < self.num_envs:
+                raise IndexError(f"env_index {i} out of range for {self.num_envs} envs")
+            i %= self.num_envs
+            sel = slice(i, i + 1)
+        rec = self._agents[sel].cpu().numpy().astype(np.uint64)
+        envs = self._envs[sel].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
         out = {
-            "grid": self._grid[:, :G, :G].cpu().numpy(),
+            "grid": self._grid[sel, :G, :G].cpu().numpy(),
             "pos": np.stack([(rec & 0xFF), ((rec >> 8) & 0xFF)], axis=-1).astype(np.uint8),
             "has_flag": ((rec >> 16) & 1).astype(np.uint8),
             "hp_q": ((rec >> 32) & 0xFFFF).astype(np.uint16).view(np.int16).astype(np.int32),
@@ -366,9 +400,9 @@ class GridworldCtfGPU:
             "captures": envs[:, 2:4].copy(),
         }
         if self._stats is not None:
-            out["stats"] = self._stats.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            out["stats"] = self._stats[sel].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
         if self._visits is not None:
-            out["visits"] = self._visits.cpu().numpy()
+            out["visits"] = self._visits[sel].cpu().numpy()
         return out
 
     def set_state(self, grid, pos, hp_q, has_flag, inventory, step, episode, captures):

@@ -9,8 +9,10 @@ handles ``B * agents_per_team`` samples.  Team-1 policies act in the flipped fra
 back by the kernel (``reverse_team1_actions=True``), as ppo.py:84-93 and utils.py:549 do with
 ``get_reversed_action`` on the host.
 
-Policies are any module with the reference ``Agent`` methods on batched inputs
-(``get_action_and_value(grid, meta, use_action_mask)``, ``get_action(...)``), e.g. ``policy.CtfPolicy``.
+Policies are any module with the reference ``Agent.get_action_and_value(grid, meta, use_action_mask)`` on batched
+inputs — the reference ``Agent`` itself (agent_network.py:63-81 is batch-safe) or ``policy.CtfPolicy``.  The duel
+adapters sample through the same method: ``Agent.get_action`` ends in ``action.item()`` (agent_network.py:58) and
+only takes one sample at a time.
 """
 from __future__ import annotations
 
@@ -63,6 +65,20 @@ def _team_indices(env, team):
     return [i for i in range(env.N_AGENTS) if env.AGENT_TEAMS[i] == team]
 
 
+def _require_dense_obs(env):
+    if env.obs is None:
+        raise ValueError("this adapter feeds policies from env.obs: create the env with dense_obs=True")
+
+
+def batched_action(policy, grid, meta, use_action_mask) -> torch.Tensor:
+    """Actions for a batch of samples from a reference-style policy: ``get_action_batch`` when the policy has one,
+    else ``get_action_and_value(...)[0]`` (same Categorical sample as ``Agent.get_action``, which is scalar-only)."""
+    fn = getattr(policy, "get_action_batch", None)
+    if fn is not None:
+        return fn(grid, meta, use_action_mask)
+    return policy.get_action_and_value(grid, meta, use_action_mask)[0]
+
+
 @torch.no_grad()
 def collect_rollout(env, agent, opponent, train_team1=True, num_env_steps=None, obs_storage_dtype=torch.float32) -> Rollout:
     """One rollout of every env (ppo.py:31-131).  ``train_team1=True`` trains team 0 (ppo.py:274-279).
@@ -72,6 +88,7 @@ def collect_rollout(env, agent, opponent, train_team1=True, num_env_steps=None, 
     stores the kernel's 1-bit-per-element copy (env created with packed_obs=True), 32x smaller than float32.
     """
     _require_folded_reversal(env)
+    _require_dense_obs(env)
     team = 0 if train_team1 else 1
     mine, theirs = _team_indices(env, team), _team_indices(env, 1 - team)
     apt = len(mine)
@@ -144,6 +161,7 @@ def batched_duel(env, agent, opponent, max_steps=256, return_result=True):
     all-reduced ``env.metrics`` dict when return_result=False (:571).
     """
     _require_folded_reversal(env)
+    _require_dense_obs(env)
     B, N, dev = env.num_envs, env.N_AGENTS, env.device
     C, G, M = env.n_channels, env.GRID_SIZE, env.meta_size
     teams = [torch.tensor(_team_indices(env, t), device=dev) for t in (0, 1)]
@@ -157,8 +175,8 @@ def batched_duel(env, agent, opponent, max_steps=256, return_result=True):
             k = idx.numel()
             if k == 0:
                 continue
-            a = pol.get_action(
-                obs[:, idx].reshape(B * k, C, G, G).float(), meta[:, idx].reshape(B * k, M),
+            a = batched_action(
+                pol, obs[:, idx].reshape(B * k, C, G, G).float(), meta[:, idx].reshape(B * k, M),
                 env.use_action_mask[idx].unsqueeze(0).expand(B, k).reshape(B * k),
             )
             actions[:, idx] = a.reshape(B, k).to(torch.uint8)

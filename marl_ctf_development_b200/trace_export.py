@@ -12,6 +12,8 @@ import json
 import numpy as np
 import torch
 
+from .rollout import _require_dense_obs, batched_action
+
 
 def _tiles(grid: np.ndarray) -> list:
     out = [{"x": int(x), "z": int(z), "type": 0} for z, x in zip(*np.where(grid == 2))]
@@ -24,11 +26,12 @@ def duel_json(env, agent, opponent, env_index=0, max_steps=256, fname=None) -> d
     """Plays one duel (utils.py:728-814) on every env of ``env`` and records env ``env_index``."""
     if not env.ce.cfg.reverse_team1_actions:
         raise ValueError("create the env with reverse_team1_actions=True")
+    _require_dense_obs(env)
     B, N, dev = env.num_envs, env.N_AGENTS, env.device
     C, G, M = env.n_channels, env.GRID_SIZE, env.meta_size
     obs, meta, _ = env.reset()
-    st = env.get_state()
-    grid0 = st["grid"][env_index]
+    st = env.get_state(env_index=env_index)   # only the recorded env leaves the device
+    grid0 = st["grid"][0]
     out = {
         "grid_size": int(env.GRID_SIZE),
         "flag_pos": {f"{k}": {"x": int(v[1]), "z": int(v[0])} for k, v in env.FLAG_POSITIONS.items()},
@@ -46,27 +49,27 @@ def duel_json(env, agent, opponent, env_index=0, max_steps=256, fname=None) -> d
     teams = [torch.tensor([i for i in range(N) if env.AGENT_TEAMS[i] == t], device=dev) for t in (0, 1)]
     actions = torch.empty((B, N), dtype=torch.uint8, device=dev)
     movement, tiles, scores = [], [], []
-    pos = st["pos"][env_index].astype(np.int64)
+    pos = st["pos"][0].astype(np.int64)
     step_count = 0
     while True:
         step_count += 1
         for idx, pol in zip(teams, (agent, opponent)):
             k = idx.numel()
             if k:
-                a = pol.get_action(
-                    obs[:, idx].reshape(B * k, C, G, G).float(), meta[:, idx].reshape(B * k, M),
+                a = batched_action(
+                    pol, obs[:, idx].reshape(B * k, C, G, G).float(), meta[:, idx].reshape(B * k, M),
                     env.use_action_mask[idx].unsqueeze(0).expand(B, k).reshape(B * k),
                 )
                 actions[:, idx] = a.reshape(B, k).to(torch.uint8)
         obs, meta, _, _, _ = env.step(actions)
         st = env.get_state()
-        new_pos = st["pos"][env_index].astype(np.int64)
+        new_pos = st["pos"][0].astype(np.int64)
         flags = st["has_flag"][env_index]
         movement.append(
             [{"x": int(new_pos[i, 1] - pos[i, 1]), "z": int(new_pos[i, 0] - pos[i, 0]), "has_flag": int(flags[i])} for i in range(N)]
         )
-        tiles.append(_tiles(st["grid"][env_index]))
-        caps = st["captures"][env_index]
+        tiles.append(_tiles(st["grid"][0]))
+        caps = st["captures"][0]
         scores.append([{"t0": int(caps[0]), "t1": int(caps[1])}])
         pos = new_pos
         if step_count > max_steps or step_count >= env.GAME_STEPS:

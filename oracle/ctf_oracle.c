@@ -40,6 +40,7 @@ typedef struct ctf_oracle_env {
     uint32_t words[32][4];
     int32_t capture_current_move;
     double capture_team_current_move[2];
+    uint32_t faults;         /* CTF_FAULT_* bits, like the device fault word */
 } ctf_oracle_env_t;
 
 /* ------------------------------------------------------------------ Philox4x32-10 */
@@ -133,7 +134,8 @@ static void respawn(ctf_oracle_env_t* e, int agent, uint32_t word) {
         for (int cc = imax(y - 1, 0); cc < imin(y + 2, G); ++cc)
             if (CELL(e, r, cc) == 0) { cand_r[k] = r; cand_c[k] = cc; ++k; }
     /* np.random.randint(k) (:771): injected pick = (word * k) >> 32. k == 0 raises ValueError in the
-       reference; it cannot happen on the shipped maps and is left as a no-move here. */
+       reference; it cannot happen on the shipped maps.  Defined behaviour of this backend (CUDA path and
+       this restatement alike): the victim stays where it is with HP <= 0 and CTF_FAULT_RESPAWN_BLOCKED is raised. */
     if (k > 0) {
         int pick = (int)(((uint64_t)word * (uint64_t)k) >> 32);
         int nr = cand_r[pick], nc = cand_c[pick]; /* == (x + di - 1, y + dj - 1) for x, y >= 1 (:775) */
@@ -149,6 +151,8 @@ static void respawn(ctf_oracle_env_t* e, int agent, uint32_t word) {
             else
                 CELL(e, c->flag_pos[1 - team][0], c->flag_pos[1 - team][1]) = c->flag_tile[1 - team];
         }
+    } else {
+        e->faults |= CTF_FAULT_RESPAWN_BLOCKED;
     }
 }
 
@@ -603,6 +607,14 @@ void ctf_oracle_batch_destroy(ctf_oracle_batch_t* bt) {
     if (!bt) return;
     free(bt->envs);
     free(bt);
+}
+
+uint32_t ctf_oracle_take_faults(ctf_oracle_env_t* e) { uint32_t f = e->faults; e->faults = 0; return f; }
+
+uint32_t ctf_oracle_batch_take_faults(ctf_oracle_batch_t* bt) {
+    uint32_t f = 0;
+    for (int b = 0; b < bt->B; ++b) f |= ctf_oracle_take_faults(&bt->envs[b]);
+    return f;
 }
 
 void ctf_oracle_batch_reset(ctf_oracle_batch_t* bt) {

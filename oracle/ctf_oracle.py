@@ -62,6 +62,10 @@ def lib():
         L.ctf_oracle_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int]
         L.ctf_oracle_batch_run.restype = C.c_double
         L.ctf_oracle_observe_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ctf_oracle_take_faults.argtypes = [C.c_void_p]
+        L.ctf_oracle_take_faults.restype = C.c_uint32
+        L.ctf_oracle_batch_take_faults.argtypes = [C.c_void_p]
+        L.ctf_oracle_batch_take_faults.restype = C.c_uint32
         _lib = L
     return _lib
 
@@ -191,6 +195,10 @@ class OracleBatch:
             self._h, None if rf is None else _p(rf), None if u8 else _p(obs), _p(obs) if u8 else None, _p(meta)
         )
         return obs, meta
+
+    def take_faults(self) -> int:
+        """CTF_FAULT_* bits raised by any env since the last call (mirrors GridworldCtfGPU.take_faults)."""
+        return int(self.L.ctf_oracle_batch_take_faults(self._h))
 
     def run(self, steps: int, seed: int, with_obs, n_threads: int) -> float:
         """Threaded continuation with uniform random actions (CPU legs of bench.py). Returns a checksum.

@@ -26,7 +26,22 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("CTF_REFERENCE_ROOT", "/root/reference")
+SRC_ROOT = os.environ.get("CTF_REFERENCE_ROOT", "/root/reference")
+# oracle/build_ref.py byte-compiles the reference's own files into oracle/_ref/*.pyc (git-ignored build output, no
+# sources): the unmodified reference then also runs where /root/reference does not exist (the GPU box)
+PYC_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _source_available() -> bool:
+    return os.path.isfile(os.path.join(SRC_ROOT, "gridworld_ctf.py"))
+
+
+def compiled_available() -> bool:
+    return os.path.isfile(os.path.join(PYC_ROOT, "gridworld_ctf.pyc"))
+
+
+REF_ROOT = SRC_ROOT if _source_available() or not compiled_available() else PYC_ROOT
+REF_SUFFIX = ".py" if REF_ROOT == SRC_ROOT else ".pyc"
 
 EXPERIMENTS = (
     "0_the_split",
@@ -42,7 +57,13 @@ EXPERIMENTS = (
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "gridworld_ctf.py"))
+    """The reference can be imported here: from its source tree, or from the byte-compiled oracle/_ref."""
+    return os.path.isfile(os.path.join(REF_ROOT, "gridworld_ctf" + REF_SUFFIX))
+
+
+def source_tree_available() -> bool:
+    """The reference's source tree itself is here (needed by the fixture generators that read json/*.json)."""
+    return REF_ROOT == SRC_ROOT and _source_available()
 
 
 class _Anything(types.ModuleType):
@@ -60,7 +81,32 @@ class _Anything(types.ModuleType):
         return _noop
 
 
-_STUB_ROOTS = ("IPython", "matplotlib", "seaborn", "imageio", "ray", "wandb", "distutils")
+_STUB_ROOTS = ("IPython", "matplotlib", "seaborn", "imageio", "wandb", "distutils")
+
+
+class _EagerRemote:
+    """``@ray.remote`` stand-in: ``f.remote(*a, **k)`` runs f at once and returns its result."""
+
+    def __init__(self, fn):
+        self._fn = fn
+
+    def remote(self, *args, **kwargs):
+        return self._fn(*args, **kwargs)
+
+    def __call__(self, *args, **kwargs):
+        return self._fn(*args, **kwargs)
+
+
+def _ray_stub():
+    """Ray is absent here; the reference's callers only need remote / get / put / init / shutdown
+    (league_training.py:16-18, 384-386, 683-687; ppo.py:264-266, 349-359).  Tasks run eagerly, in submission order."""
+    mod = types.ModuleType("ray")
+    mod.remote = lambda fn: _EagerRemote(fn)
+    mod.get = lambda x: x
+    mod.put = lambda x: x
+    mod.init = lambda *a, **k: None
+    mod.shutdown = lambda *a, **k: None
+    return mod
 
 
 class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
@@ -90,6 +136,8 @@ def _install_stubs():
             missing.append(name)
     if missing:
         sys.meta_path.append(_StubFinder(tuple(missing)))
+    if importlib.util.find_spec("ray") is None and "ray" not in sys.modules:
+        sys.modules["ray"] = _ray_stub()
 
 
 @contextlib.contextmanager
@@ -101,6 +149,15 @@ def _in_ref_dir():
         yield
     finally:
         os.chdir(old)
+
+
+class _NoSprites:
+    """Stands in for PIL.Image inside gridworld_ctf where the sprite folder is absent (oracle/_ref holds no assets):
+    the ctor only stores the 24 opened images for render_image (gridworld_ctf.py:319-347, out of scope)."""
+
+    @staticmethod
+    def open(path):
+        return None
 
 
 _modules = {}
@@ -117,14 +174,27 @@ def reference_modules():
         with _in_ref_dir():
             _modules["gw"] = importlib.import_module("gridworld_ctf")
             _modules["scn"] = importlib.import_module("scenarios")
+        if not os.path.isdir(os.path.join(REF_ROOT, "img")):
+            _modules["gw"].Image = _NoSprites
     return _modules["gw"], _modules["scn"]
+
+
+def caller_modules() -> dict:
+    """The reference's callers of the step path, unmodified: ppo (PPOTrainer), utils (duel, duel_json),
+    league_training (LeagueTrainer), agent_network (Agent), metrics_logger (MetricsLogger)."""
+    reference_modules()
+    if "ppo" not in _modules:
+        with _in_ref_dir():
+            for name in ("agent_network", "metrics_logger", "utils", "ppo", "league_training"):
+                _modules[name] = importlib.import_module(name)
+    return {k: _modules[k] for k in ("agent_network", "metrics_logger", "utils", "ppo", "league_training")}
 
 
 def experiment_env_config(name: str) -> dict:
     """``TrainingConfig().env_config`` of an experiment script (e.g. '8_arena')."""
     reference_modules()
     with _in_ref_dir():
-        ns = runpy.run_path(os.path.join(REF_ROOT, name + ".py"), run_name="ctf_ref_shim")
+        ns = runpy.run_path(os.path.join(REF_ROOT, name + REF_SUFFIX), run_name="ctf_ref_shim")
     return ns["TrainingConfig"]().env_config
 
 
@@ -207,9 +277,17 @@ def injected_env_class():
     gw.np = _NumpyProxy(_hub)
 
     class InjectedGridworldCtf(gw.GridworldCtf):
-        def __init__(self, *args, seed=0, env_id=0, **kwargs):
+        def __init__(self, *args, seed=0, env_id=0, reset_advances="episode", **kwargs):
+            # reset_advances="episode": every reset() starts the next episode of env `env_id` (how one GPU env behaves).
+            # reset_advances="env": the ctor's reset is (env_id, episode 0); the k-th later reset() becomes episode 1 of
+            # env `env_id + k - 1` — a caller that plays one duel after the other on ONE env object (league_training.py
+            # submits number_of_duels tasks with the same env) then visits the same draws as a GPU batch whose env
+            # env_id + k - 1 plays duel k after the batch-wide reset.
             self._inj_seed = int(seed)
             self._inj_env_id = int(env_id)
+            self._inj_first_env_id = int(env_id)
+            self._inj_reset_advances = reset_advances
+            self._inj_resets = -1
             self._inj_episode = -1
             self._inj_words = None
             self._inj_shuffles = 0
@@ -235,7 +313,12 @@ def injected_env_class():
 
         # -- hooks ------------------------------------------------------------------
         def reset(self):
-            self._inj_episode += 1
+            self._inj_resets += 1
+            if self._inj_reset_advances == "env" and self._inj_resets >= 1:
+                self._inj_env_id = self._inj_first_env_id + self._inj_resets - 1
+                self._inj_episode = 1
+            else:
+                self._inj_episode += 1
             _hub.env = self
             return super().reset()
 
@@ -256,8 +339,8 @@ def injected_env_class():
     return _injected_cls
 
 
-def make_injected_env(env_config: dict, seed: int = 0, env_id: int = 0):
-    return injected_env_class()(**env_config, seed=seed, env_id=env_id)
+def make_injected_env(env_config: dict, seed: int = 0, env_id: int = 0, reset_advances: str = "episode"):
+    return injected_env_class()(**env_config, seed=seed, env_id=env_id, reset_advances=reset_advances)
 
 
 # --------------------------------------------------------------------------------------

@@ -1,39 +1,18 @@
 """Drop-in adapters on the GPU: the single-env view with the reference's surface, and the batched
-rollout / duel loops, each checked against the reference's caller loops run on the oracle."""
+rollout / duel loops against the same loops on the CPU oracle at larger batch sizes.  The loops
+themselves are pinned to the reference's UNMODIFIED callers by tests/test_gpu_callers.py (fixtures generated from
+ppo.py / utils.py / league_training.py) and tests/test_callers_fixtures.py (the oracle-side loops vs those fixtures)."""
 import numpy as np
 import pytest
 import torch
 
 import traces
+from hash_policy import HashPolicy
 from helpers import bits, compiled, golden_traces
 from marl_ctf_development_b200 import experiment_env_config
 from oracle.ctf_oracle import OracleBatch, OracleEnv
 
 pytestmark = pytest.mark.gpu
-
-
-class HashPolicy(torch.nn.Module):
-    """Deterministic integer 'policy': the action is an exact hash of (observation, metadata, mask flag).
-
-    Exact in float64 on CPU and GPU alike, so the batched loops can be compared with per-env loops."""
-
-    def __init__(self, n_obs, n_meta, salt):
-        super().__init__()
-        g = torch.Generator().manual_seed(salt)
-        self.register_buffer("w1", torch.randint(1, 97, (n_obs,), generator=g).double())
-        self.register_buffer("w2", torch.randint(1, 97, (n_meta,), generator=g).double())
-
-    def _act(self, grid, meta, use_action_mask):
-        h = grid.double().flatten(1) @ self.w1 + (meta.double() * 64).round() @ self.w2
-        n = torch.where(use_action_mask.reshape(-1) == 1, 5, 9).double()
-        return (h - torch.floor(h / n) * n).long()
-
-    def get_action(self, grid, meta, use_action_mask):
-        return self._act(grid, meta, use_action_mask)
-
-    def get_action_and_value(self, grid, meta, use_action_mask, action=None):
-        a = self._act(grid, meta, use_action_mask)
-        return a, -a.float() / 8, torch.zeros_like(a, dtype=torch.float32), (a.float() * 0.5).unsqueeze(1)
 
 
 def _reference_style_rollout(ce, B, seed, agent, opponent, train_team1, T):

@@ -607,3 +607,136 @@ def test_soak_every_experiment_full_episode_with_visits(exp):
             _assert_obs(env, orc, f"{exp} t={t}", u8=True)
     st, so = env.get_state(), orc.state()
     assert np.array_equal(st["stats"], so["stats"]) and np.array_equal(st["visits"], so["visits"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the persistent warp-specialised kernel (k_step_ws): same results as the warp-per-env kernel and the oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture
+def force_persistent_kernel(monkeypatch):
+    """ctf_create reads these: every batch size and output type then runs k_step_ws (default: large float32 batches)."""
+    monkeypatch.setenv("CTF_WS", "1")
+    monkeypatch.setenv("CTF_WS_MIN_ENVS", "1")
+
+
+@pytest.mark.parametrize("exp,B,dtype,policy", [
+    ("8_arena", 3000, torch.float32, "seek"),          # ~2.5 envs per logic warp: buffers are reused, FIFO wraps
+    ("7_gridlocked", 2500, torch.float32, "builder"),  # 8-byte aligned env blocks: padded bit strings, scalar head / tail
+    ("0_the_split", 5000, torch.uint8, "uniform"),
+    ("8_arena", 1500, torch.bfloat16, "uniform"),
+    ("5_skittles", 7, torch.float32, "seek"),          # fewer envs than logic warps
+])
+def test_persistent_kernel_against_oracle(force_persistent_kernel, exp, B, dtype, policy):
+    env, _ = _run_against_oracle(exp, B, 40, policy, seed=21, obs_every=13, stats="full", obs_dtype=dtype)
+    assert env.uses_persistent_kernel
+    info = env.kernel_info()
+    assert info.ctas >= 1 and info.logic_warps + info.stream_warps <= 32
+
+
+def test_persistent_kernel_is_the_default_only_for_large_float32_blocks(monkeypatch):
+    for k in ("CTF_WS", "CTF_WS_MIN_ENVS"):
+        monkeypatch.delenv(k, raising=False)
+    assert not _env("8_arena", 64).uses_persistent_kernel                      # too few envs
+    assert not _env("0_the_split", 20000).uses_persistent_kernel               # small observation blocks: logic-bound
+    assert not _env("8_arena", 20000, obs_dtype=torch.uint8).uses_persistent_kernel
+    big = _env("8_arena", 20000)
+    assert big.uses_persistent_kernel
+    small = _env("8_arena", 20000)
+    monkeypatch.setenv("CTF_WS", "0")
+    other = _env("8_arena", 20000)
+    assert not other.uses_persistent_kernel
+    acts = torch.randint(0, 9, (6, 20000, 8), dtype=torch.uint8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    for t in range(6):
+        big.step(acts[t])
+        other.step(acts[t])
+    assert torch.equal(big.obs, other.obs) and torch.equal(big.meta, other.meta) and torch.equal(big.rewards, other.rewards)
+    assert torch.equal(big._grid, other._grid) and torch.equal(big._agents, other._agents)
+    del small
+
+
+def test_persistent_kernel_packed_outputs_and_graph_replay(force_persistent_kernel):
+    """The env counter re-arms itself at the end of every launch, so captured launches replay; packed + dense outputs agree."""
+    B = 2000
+    eager = _env("8_arena", B, seed=8, stats="counters", packed_obs=True)
+    graphed = _env("8_arena", B, seed=8, stats="counters", packed_obs=True, validate_actions=True)
+    assert eager.uses_persistent_kernel
+    acts = torch.zeros((B, 8), dtype=torch.uint8, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    graph = graphed.make_step_graph(acts, steps_per_replay=1)   # validate_actions is suspended inside the capture
+    for _ in range(25):
+        acts.copy_(torch.randint(0, 9, acts.shape, dtype=torch.uint8, device="cuda", generator=gen))
+        eager.step(acts)
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(eager.obs, graphed.obs) and torch.equal(eager.obs_bits, graphed.obs_bits)
+    assert torch.equal(eager.unpack_obs(eager.obs_bits), eager.obs)
+    se, sg = eager.get_state(), graphed.get_state()
+    for k in STATE_KEYS + ("step", "stats"):
+        assert np.array_equal(se[k], sg[k]), k
+
+
+# ---------------------------------------------------------------------------------------------------
+# defined behaviour where the reference raises: a lethal tag with a full spawn window (gridworld_ctf.py:771)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("persistent", [False, True])
+def test_respawn_into_a_full_spawn_window_sets_the_fault_bit(monkeypatch, persistent):
+    from marl_ctf_development_b200 import _native
+
+    if persistent:
+        monkeypatch.setenv("CTF_WS", "1")
+        monkeypatch.setenv("CTF_WS_MIN_ENVS", "1")
+    B = 6
+    env = _env("0_the_split", B, seed=3, env_id_base=50, env_overrides={"AGENT_TYPE_DAMAGE": {0: 100, 1: 100, 2: 100, 3: 100}, "TAG_PROBABILITY": 1.0})
+    ce = env.ce
+    orc = OracleBatch(ce, B, seed=3, env_id_base=50)
+    st = orc.state()
+    G = ce.GRID_SIZE
+    grid = st["grid"].copy()
+    pos = st["pos"].copy()
+    # wall in team 1's spawn window completely, and put agents 0 (team 0) and 1 (team 1) next to each other elsewhere
+    sx, sy = ce.SPAWN_POSITIONS[1]
+    for b in range(B):
+        for i in range(ce.N_AGENTS):
+            grid[b, pos[b, i, 0], pos[b, i, 1]] = 0
+        grid[b, max(sx - 1, 0):sx + 2, max(sy - 1, 0):sy + 2] = 1
+        free = [(r, c) for r in range(G) for c in range(G - 1) if grid[b, r, c] == 0 and grid[b, r, c + 1] == 0]
+        cells = [free[0], (free[0][0], free[0][1] + 1)] + [f for f in free[4:] if f[0] != free[0][0]][: ce.N_AGENTS - 2]
+        for i, (r, c) in enumerate(cells):
+            pos[b, i] = (r, c)
+            grid[b, r, c] = ce.AGENT_TILE_MAP[i]
+    args = dict(grid=grid, pos=pos, hp_q=st["hp_q"], has_flag=st["has_flag"], inventory=st["inventory"], step=st["step"],
+                episode=st["episode"], captures=st["captures"])
+    orc.set_state(**args)
+    env.set_state(**args)
+    a = np.full((B, ce.N_AGENTS), 4, dtype=np.uint8)
+    _, _, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+    r_ref, _ = orc.step(a)
+    assert np.array_equal(bits(rew.cpu().numpy()), bits(r_ref))
+    _assert_batch_state(env, orc, "blocked respawn")
+    assert (orc.state()["hp_q"] <= 0).any()                      # a victim was left in place with HP <= 0
+    assert orc.take_faults() & _native.FAULT_RESPAWN_BLOCKED
+    assert env.take_faults() == _native.FAULT_RESPAWN_BLOCKED and env.take_faults() == 0
+    env.step(torch.from_numpy(a).cuda())
+    with pytest.raises(ValueError):
+        env.raise_on_faults()
+
+
+def test_get_state_of_selected_envs_and_current_device_is_preserved():
+    env = _env("7_gridlocked", 300, seed=4)
+    a = torch.randint(0, 9, (300, env.N_AGENTS), dtype=torch.uint8, device="cuda")
+    for _ in range(5):
+        env.step(a)
+    full = env.get_state()
+    one = env.get_state(env_index=17)
+    some = env.get_state(env_index=slice(10, 20))
+    for k in full:
+        assert np.array_equal(one[k], full[k][17:18]) and np.array_equal(some[k], full[k][10:20]), k
+    assert np.array_equal(env.get_state(env_index=-1)["grid"], full["grid"][-1:])
+    with pytest.raises(IndexError):
+        env.get_state(env_index=300)
+    if torch.cuda.device_count() > 1:   # entry points run on the env's device and restore the caller's (ADVICE r1)
+        with torch.cuda.device(1):
+            env.step(a)
+            assert torch.cuda.current_device() == 1
+            assert torch.empty(1, device="cuda").device.index == 1
+    assert torch.cuda.current_device() == 0
