@@ -4,10 +4,12 @@
     python bench_rollout.py [--envs B] [--steps K] [--warmup W] [--policy-dtype bf16|fp32] [--chunk S]
     torchrun --nproc-per-node N bench_rollout.py ...      (env sharding, one rank per GPU)
 
-Reports, as one JSON line from rank 0, agent-steps/s of the whole loop (policy forward for both teams on the
-observation buffers the step kernel wrote, action sampling, env.step) next to the env-only figure.  This is a
-functional integration of SURVEY §8f row N1: the policy is stock torch/cuDNN (≈3.9 MFLOP per agent-step) and
-dominates the time; it is outside the hot path this repo accelerates, so this number is not the headline.
+Reports, as one JSON line from rank 0, agent-steps/s of the whole loop — policy forward for both teams on the
+observation buffers the step kernel wrote, action sampling, env.step, and the packed (1 bit per element) copy of the
+trained team's observations stored into a rollout ring buffer — next to the env-only and the policy-only figures.
+With --graph the whole loop body (both policy forwards + step + store) is captured in ONE CUDA graph and replayed.
+This is a functional integration of SURVEY §8f row N1: the policy is stock torch/cuDNN (≈3.9 MFLOP per agent-step)
+and dominates the time; it is outside the hot path this repo accelerates, so this number is not the headline.
 """
 from __future__ import annotations
 
@@ -29,7 +31,9 @@ def main():
     from marl_ctf_development_b200.policy import CtfPolicy
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("--envs", type=int, default=8192)
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU (BASELINE.json config 5: 65536)")
+    ap.add_argument("--graph", action="store_true", help="capture policy forwards + step + rollout store in one CUDA graph")
+    ap.add_argument("--store-steps", type=int, default=16, help="depth of the packed rollout ring buffer (env steps)")
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--policy-dtype", choices=["bf16", "fp32"], default="bf16")
@@ -49,7 +53,7 @@ def main():
     obs_dtype = args.obs_dtype or ("bfloat16" if args.policy_dtype == "bf16" else "float32")
     torch.backends.cudnn.benchmark = True
     env = GridworldCtfGPU(**experiment_env_config("8_arena"), num_envs=B, device=dev, seed=0, env_id_base=rank * B,
-                          reverse_team1_actions=True, stats="counters", obs_dtype=getattr(torch, obs_dtype))
+                          reverse_team1_actions=True, stats="counters", obs_dtype=getattr(torch, obs_dtype), packed_obs=True)
     N, C, G, M = env.N_AGENTS, env.n_channels, env.GRID_SIZE, env.meta_size
     torch.manual_seed(rank)
     pols = [CtfPolicy(9, C, G, M).to(dev).eval() for _ in range(2)]
@@ -74,20 +78,51 @@ def main():
                     outs.append(pol.get_action(g[s : s + args.chunk], m[s : s + args.chunk], f[s : s + args.chunk]))
             actions[:, idx] = torch.cat(outs).reshape(B, k).to(torch.uint8)
 
-    def run(k_steps, with_policy):
-        obs, meta = env.obs, env.meta
-        for _ in range(k_steps):
-            if with_policy:
-                policy_step(obs, meta)
-            obs, meta, _, dones, _ = env.step(actions)
+    # packed rollout storage of the trained team (team 0): [store_steps, apt, B, words_per_agent] int32, 32x smaller than
+    # float32 (a float32 [500*4, 65536, 14, 15, 15] rollout would be 1.6 PB); unpacked per minibatch at update time
+    apt = int(teams[0].numel())
+    ring = torch.zeros((args.store_steps, apt, B, env.bits_words_per_agent), dtype=torch.int32, device=dev)
+    ring_meta = torch.zeros((args.store_steps, apt, B, M), dtype=torch.float32, device=dev)
+    slot = [0]
 
-    def timed(k_steps, with_policy):
+    def body(with_policy=True, with_env=True):
+        if with_policy:
+            policy_step(env.obs, env.meta)
+        if with_env:
+            k = slot[0] % args.store_steps
+            ring[k].copy_(env.obs_bits[:, teams[0]].transpose(0, 1))
+            ring_meta[k].copy_(env.meta[:, teams[0]].transpose(0, 1))
+            slot[0] += 1
+            env.step(actions)
+
+    graphs = {}
+
+    def run(k_steps, with_policy, with_env=True):
+        key = (with_policy, with_env)
+        if args.graph and key not in graphs:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                body(with_policy, with_env)           # warm-up outside the capture (cuDNN autotune, allocator)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body(with_policy, with_env)
+            graphs[key] = g
+        for _ in range(k_steps):
+            if args.graph:
+                graphs[key].replay()
+            else:
+                body(with_policy, with_env)
+
+    def timed(k_steps, with_policy, with_env=True):
+        run(1, with_policy, with_env)                 # graph capture / first call outside the timed region
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        run(k_steps, with_policy)
+        run(k_steps, with_policy, with_env)
         e1.record()
         torch.cuda.synchronize(dev)
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -100,15 +135,21 @@ def main():
     run(args.warmup, True)
     ms_full = timed(args.steps, True)
     ms_env = timed(args.steps, False)
+    ms_pol = timed(args.steps, True, False)
     if rank == 0:
         total = world * B * N * args.steps
         print(json.dumps({
             "metric": "rollout_agent_steps_per_sec", "value": total / (ms_full * 1e-3), "unit": "agent-steps/s",
-            "env_only_value": total / (ms_env * 1e-3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_full / args.steps, "env_ms_per_step": ms_env / args.steps,
+            "env_only_value": total / (ms_env * 1e-3), "policy_only_value": total / (ms_pol * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_full / args.steps, "env_ms_per_step": ms_env / args.steps, "policy_ms_per_step": ms_pol / args.steps,
+            "cuda_graph": bool(args.graph),
+            "rollout_storage": f"packed observations of the trained team, ring of {args.store_steps} steps: "
+                               f"{ring.numel() * 4 / 1e6:.0f} MB (float32 would be {ring.numel() * 4 * 32 / 1e9:.1f} GB)",
             "config": {"workload": f"8_arena self-play rollout, B={B} envs/GPU, CtfPolicy (agent_network.py architecture) "
                                    f"for both teams, policy dtype {args.policy_dtype}, {obs_dtype} observations"
-                                   f"{', channels_last' if args.channels_last else ''}", "envs_per_gpu": B},
+                                   f"{', channels_last' if args.channels_last else ''}; env-only = step + packed rollout store",
+                       "envs_per_gpu": B},
             "data": "synthetic (random-init policies)",
         }), flush=True)
     if world > 1:

@@ -62,9 +62,9 @@ def duel_json(env, agent, opponent, env_index=0, max_steps=256, fname=None) -> d
                 )
                 actions[:, idx] = a.reshape(B, k).to(torch.uint8)
         obs, meta, _, _, _ = env.step(actions)
-        st = env.get_state()
+        st = env.get_state(env_index=env_index)
         new_pos = st["pos"][0].astype(np.int64)
-        flags = st["has_flag"][env_index]
+        flags = st["has_flag"][0]
         movement.append(
             [{"x": int(new_pos[i, 1] - pos[i, 1]), "z": int(new_pos[i, 0] - pos[i, 0]), "has_flag": int(flags[i])} for i in range(N)]
         )

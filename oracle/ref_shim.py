@@ -27,7 +27,7 @@ import types
 import numpy as np
 
 SRC_ROOT = os.environ.get("CTF_REFERENCE_ROOT", "/root/reference")
-# oracle/build_ref.py byte-compiles the reference's own files into oracle/_ref/*.pyc (git-ignored build output, no
+# oracle/build_ref.py byte-compiles the reference's own files into oracle/_ref/*.refc (git-ignored build output, no
 # sources): the unmodified reference then also runs where /root/reference does not exist (the GPU box)
 PYC_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
@@ -37,11 +37,22 @@ def _source_available() -> bool:
 
 
 def compiled_available() -> bool:
-    return os.path.isfile(os.path.join(PYC_ROOT, "gridworld_ctf.pyc"))
+    return os.path.isfile(os.path.join(PYC_ROOT, "gridworld_ctf.refc"))
 
 
 REF_ROOT = SRC_ROOT if _source_available() or not compiled_available() else PYC_ROOT
-REF_SUFFIX = ".py" if REF_ROOT == SRC_ROOT else ".pyc"
+REF_SUFFIX = ".py" if REF_ROOT == SRC_ROOT else ".refc"
+
+
+class _CompiledRefFinder(importlib.abc.MetaPathFinder):
+    """Imports ``import gridworld_ctf`` etc. from oracle/_ref/<name>.refc (byte code written by py_compile)."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        cand = os.path.join(PYC_ROOT, fullname + ".refc")
+        if "." in fullname or not os.path.isfile(cand):
+            return None
+        loader = importlib.machinery.SourcelessFileLoader(fullname, cand)
+        return importlib.util.spec_from_file_location(fullname, cand, loader=loader)
 
 EXPERIMENTS = (
     "0_the_split",
@@ -169,8 +180,11 @@ def reference_modules():
         raise RuntimeError(f"reference not found under {REF_ROOT}")
     if not _modules:
         _install_stubs()
-        if REF_ROOT not in sys.path:
-            sys.path.insert(0, REF_ROOT)
+        if REF_SUFFIX == ".py":
+            if REF_ROOT not in sys.path:
+                sys.path.insert(0, REF_ROOT)
+        elif not any(isinstance(f, _CompiledRefFinder) for f in sys.meta_path):
+            sys.meta_path.insert(0, _CompiledRefFinder())
         with _in_ref_dir():
             _modules["gw"] = importlib.import_module("gridworld_ctf")
             _modules["scn"] = importlib.import_module("scenarios")

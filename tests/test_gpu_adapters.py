@@ -236,7 +236,7 @@ def test_json_trace_export_matches_reference_wire_format(tmp_path):
         acts = np.zeros((1, N), dtype=np.uint8)
         for i in range(N):
             pol = agent if ce.AGENT_TEAMS[i] == 0 else opponent
-            a = int(pol.get_action(torch.from_numpy(obs[:, i]), torch.from_numpy(meta[:, i]), flags[i].expand(1))[0])
+            a = int(pol.get_action(torch.from_numpy(obs[:, i]), torch.from_numpy(meta[:, i]), flags[i].expand(1)))   # one sample: a Python int, like Agent.get_action
             acts[0, i] = rev[a] if ce.AGENT_TEAMS[i] == 1 else a
         orc.step(acts)
         st = orc.state()
