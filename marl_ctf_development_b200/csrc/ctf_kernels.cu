@@ -345,7 +345,9 @@ __device__ __forceinline__ void stream_vectors(const uint32_t* __restrict__ bits
     if constexpr (sizeof(T) == 4) {
         // group g = 128 vectors = 16 words = 2 KB of output: lane (q, n) = (lane >> 3, lane & 7) reads words
         // 16g + 4q .. +3 with ONE 128-bit shared load and stores vector 8 * (16g + 4q + m) + n for m = 0..3, so every
-        // store instruction writes four complete 128-byte lines
+        // store instruction writes four complete 128-byte runs.  The per-store bounds checks stay on purpose: a loop
+        // without them (and with the next group's load issued early) executes 40 % fewer instructions but is 1 - 7 %
+        // SLOWER (profiles/r02_ab_stream_loop*.log) — the HBM write stream likes stores spaced out, not bursts of four
         const int q = lane >> 3, n = lane & 7, sh = n * 4;
         const int n_groups = (v_end + 127) >> 7;
 #pragma unroll 2

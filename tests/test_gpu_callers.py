@@ -61,6 +61,8 @@ def test_batched_duel_equals_unmodified_utils_duel(case):
     assert np.array_equal(env.counters().cpu().numpy(), want["counters"])                            # env.metrics of every duel
     assert np.array_equal(env.flag_captures().cpu().numpy(), want["captures"])
     assert np.array_equal(env.step_counts().cpu().numpy(), want["steps"])
+    env = GridworldCtfGPU(**cc.env_config(exp, overrides), num_envs=n, device="cuda:0", seed=cc.SEED, env_id_base=env_id0,
+                          reverse_team1_actions=True, stats="counters")   # a fresh env: the duel's reset starts episode 1 again
     metrics = batched_duel(env, agent, opponent, max_steps=max_steps, return_result=False)           # utils.py:571, summed over envs
     for k, mname in enumerate(METRIC_NAMES):
         for i in range(env.N_AGENTS):

@@ -716,9 +716,18 @@ def test_respawn_into_a_full_spawn_window_sets_the_fault_bit(monkeypatch, persis
     assert (orc.state()["hp_q"] <= 0).any()                      # a victim was left in place with HP <= 0
     assert orc.take_faults() & _native.FAULT_RESPAWN_BLOCKED
     assert env.take_faults() == _native.FAULT_RESPAWN_BLOCKED and env.take_faults() == 0
-    env.step(torch.from_numpy(a).cuda())
+    # later steps keep agreeing with the oracle, fault word included
+    for _ in range(3):
+        env.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+        assert env.take_faults() == orc.take_faults()
+    _assert_batch_state(env, orc, "after blocked respawns")
+    # validate_actions=True turns the bit into the reference's exception type
+    strict = _env("0_the_split", B, seed=3, env_id_base=50, validate_actions=True,
+                  env_overrides={"AGENT_TYPE_DAMAGE": {0: 100, 1: 100, 2: 100, 3: 100}, "TAG_PROBABILITY": 1.0})
+    strict.set_state(**args)
     with pytest.raises(ValueError):
-        env.raise_on_faults()
+        strict.step(torch.from_numpy(a).cuda())
 
 
 def test_get_state_of_selected_envs_and_current_device_is_preserved():
