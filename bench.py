@@ -387,9 +387,9 @@ def run_ours(args) -> dict | None:
         graph = env.make_step_graph(actions[0], steps_per_replay=args.graph_steps)
     # ---- timed region: K steps, CUDA events on the launching stream, barrier + synchronize on both sides; the
     # statistics of the steps so far are reduced (device sum + NCCL all-reduce over ranks) inside it, after step K
+    sampler = ClockSampler(local_rank)   # NVML initialisation BEFORE the barrier: it takes milliseconds and differs per rank,
+    sampler.sample()                     # and a late starter would make every other rank wait at the all-reduce below
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.sample()
     sampler.start()
     launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

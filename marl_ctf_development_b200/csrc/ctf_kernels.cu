@@ -834,6 +834,9 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
 #define CTF_PROF_T(var)
 #define CTF_PROF_ADD(acc, t0, t1)
 #endif
+#ifndef CTF_WS_SLEEP_NS
+#define CTF_WS_SLEEP_NS 32       // back-off of the FIFO / buffer polls
+#endif
 constexpr int kWsQ = 32;         // FIFO slots (>= logic warps per CTA)
 constexpr int kWsCtlBytes = 1024;
 struct WsCtl {
@@ -876,7 +879,7 @@ __global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ Dev
             const uint32_t me = step_env<STATS>(P, L, w, (long long)e, lane, rev_mask);
             if (!any_obs) continue;
             CTF_PROF_T(t2);
-            if (lane == 0) while (c->busy[warp]) __nanosleep(32);   // previous env of this warp still being streamed
+            if (lane == 0) while (c->busy[warp]) __nanosleep(CTF_WS_SLEEP_NS);   // previous env of this warp still being streamed
             __syncwarp();
             CTF_PROF_T(t3);
             const int pad = L.obs ? obs_pad(reinterpret_cast<T*>(L.obs) + (long long)e * P.E) : 0;
@@ -885,7 +888,7 @@ __global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ Dev
                 c->busy[warp] = 1;
                 const int t = atomicAdd(&c->tail, 1);
                 const int slot = t % kWsQ;
-                while (c->ready[slot] != 0) __nanosleep(32);
+                while (c->ready[slot] != 0) __nanosleep(CTF_WS_SLEEP_NS);
                 c->env[slot] = (int)e;
                 c->buf[slot] = warp;
                 __threadfence_block();
@@ -913,7 +916,7 @@ __global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ Dev
                 for (;;) {
                     if (c->ready[slot] == head + 1) { got = 1; break; }
                     if (*(volatile int*)&c->producers == 0 && *(volatile int*)&c->tail == head) break;
-                    __nanosleep(32);
+                    __nanosleep(CTF_WS_SLEEP_NS);
                 }
                 __threadfence_block();
             }

@@ -45,14 +45,15 @@ class CtfPolicy(nn.Module):
 
     def get_action_and_value(self, grid, meta, use_action_mask, action=None):
         value, logits = self(grid, meta)
-        probs = Categorical(logits=self.masked_logits(logits, use_action_mask))
+        probs = Categorical(logits=self.masked_logits(logits, use_action_mask), validate_args=False)
         if action is None:
             action = probs.sample()
         return action, probs.log_prob(action), probs.entropy(), value
 
     def get_action(self, grid, meta, use_action_mask):
         _, logits = self(grid, meta)
-        return Categorical(logits=self.masked_logits(logits, use_action_mask)).sample()
+        # validate_args=False: the argument check reads a flag back to the host, which a CUDA graph capture forbids
+        return Categorical(logits=self.masked_logits(logits, use_action_mask), validate_args=False).sample()
 
     def get_value(self, grid, meta):
         return self(grid, meta)[0]
