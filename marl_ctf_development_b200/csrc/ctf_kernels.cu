@@ -1366,8 +1366,10 @@ extern "C" int ctf_unpack_obs(ctf_handle_t h, const uint32_t* packed, void* out,
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int nbits = h->plan.C * h->plan.GG, wpa = h->plan.wpa;
     const int elem = out_dtype == CTF_OBS_F32 ? 4 : (out_dtype == CTF_OBS_U8 ? 1 : 2);
-    int chunk = (96 * 1024) / (nbits * elem);          // ~96 KB of output per CTA
+    static const int chunk_kb = env_int("CTF_UNPACK_CHUNK_KB", 48);   // 12 .. 384 KB swept: profiles/r02_unpack_chunk_sweep.log
+    int chunk = (chunk_kb * 1024) / (nbits * elem);    // ~48 KB of output per CTA
     chunk = chunk < 1 ? 1 : (chunk > 64 ? 64 : chunk);
+    while (chunk > 1 && ((size_t)(chunk * nbits) / 8 + (size_t)chunk * wpa * 4) > 40 * 1024) --chunk;   // static shared-memory budget
     const int bits_words = (((chunk * nbits + 128 + 31) / 32 + 1) + 15) / 16 * 16;
     const unsigned grid = (unsigned)((n_agent_blocks + chunk - 1) / chunk);
     const size_t smem = ((size_t)bits_words + (size_t)chunk * wpa) * sizeof(uint32_t);
