@@ -62,6 +62,7 @@ struct DevPlan {
     int bits_words;               // words of the per-env observation bit string (alignment pad + slack, multiple of 16)
     int wpa;                      // words per agent of the packed observation output: ceil(C*G*G / 32)
     int game_steps, flip_axis;
+    int flip_a, flip_b, flip_d;    // flipped cell index = flip_a * r + flip_b * c + flip_d
     int use_adjusted_rewards, home_flag_capture, drop_flag_when_no_hp, reverse_team1_actions;
     int heal_q, vault_cost_q, vault_min_q;
     int zone_distance, guardian_distance, tagging_range, max_agent_blocks, block_pickup_value;
@@ -74,6 +75,7 @@ struct DevPlan {
     signed char delta[4][9][2];
     unsigned char rev_action[16];
     unsigned int meta_row[8];        // metadata slots of observer a: nibble q -> agent id (0xF = none)
+    unsigned int meta_codes[64];     // kMeta* code of every element of the [N][M] metadata block, four per word
     unsigned char grid_template[kGridBytes];  // 16-stride rows
 };
 
@@ -143,17 +145,8 @@ __device__ __forceinline__ WarpMem warp_mem(const DevPlan& P, unsigned char* sme
 }
 
 // flipped destination cell of (r, c) for a reversed view (gridworld_ctf.py:1003-1007); all four maps are involutions
-__device__ __forceinline__ int flip_cell(const DevPlan& P, int r, int c) {
-    const int G1 = P.G - 1;
-    int fr, fc;
-    switch (P.flip_axis) {
-        case -1: fr = G1 - r; fc = G1 - c; break;
-        case 0: fr = G1 - r; fc = c; break;
-        case 1: fr = r; fc = G1 - c; break;
-        default: fr = G1 - c; fc = G1 - r; break;
-    }
-    return fr * P.G + fc;
-}
+// and affine in (r, c): the host folds FLIP_AXIS into three coefficients (build_plan)
+__device__ __forceinline__ int flip_cell(const DevPlan& P, int r, int c) { return P.flip_a * r + P.flip_b * c + P.flip_d; }
 
 // ------------------------------------------------------------------------------------------------
 // Observation + metadata writer (standardise_state :975-1009, get_env_metadata :1027-1069)
@@ -337,11 +330,32 @@ __device__ __forceinline__ int obs_pad(const T* out) {
     return (int)((reinterpret_cast<uintptr_t>(out) & (uintptr_t)(CTF_PAD_BYTES - 1)) / sizeof(T));
 }
 
+#ifndef CTF_U8_LUT
+#define CTF_U8_LUT 1   // uint8 stream: expand 8 bits -> 8 bytes with one 64-bit shared load from a 256-entry table
+#endif
+// bytes at the start of a kernel's dynamic shared memory taken by the expansion table of element type T
+template <typename T>
+constexpr int kLutBytes = (CTF_U8_LUT && sizeof(T) == 1) ? 2048 : 0;
+
+// Fills the table (all threads of the CTA, before any thread leaves the kernel); returns it, or nullptr for other types.
+template <typename T>
+__device__ __forceinline__ const uint2* init_expand_lut(uint4* smem_raw) {
+    if constexpr (kLutBytes<T> > 0) {
+        uint2* lut = reinterpret_cast<uint2*>(smem_raw);
+        for (unsigned i = threadIdx.x; i < 256u; i += blockDim.x)
+            lut[i] = make_uint2(((i & 15u) * 0x00204081u) & 0x01010101u, ((i >> 4) * 0x00204081u) & 0x01010101u);
+        __syncthreads();
+        return lut;
+    } else {
+        return nullptr;
+    }
+}
+
 // Stores the full vectors [v_begin, v_end) of a padded bit string (vector v = bits VB*v .. VB*v + VB - 1) at vp[v];
 // warp `wi` of `nw` cooperating warps.  `bits` must be 16-byte aligned and readable up to a multiple of 16 words.
 template <typename T>
 __device__ __forceinline__ void stream_vectors(const uint32_t* __restrict__ bits, uint4* __restrict__ vp, int v_begin,
-                                               int v_end, int wi, int nw, int lane) {
+                                               int v_end, int wi, int nw, int lane, const uint2* __restrict__ lut) {
     if constexpr (sizeof(T) == 4) {
         // group g = 128 vectors = 16 words = 2 KB of output: lane (q, n) = (lane >> 3, lane & 7) reads words
         // 16g + 4q .. +3 with ONE 128-bit shared load and stores vector 8 * (16g + 4q + m) + n for m = 0..3, so every
@@ -361,9 +375,21 @@ __device__ __forceinline__ void stream_vectors(const uint32_t* __restrict__ bits
         }
     } else {
         constexpr int VB = kVecElems<T>, VW = 32 / VB;
+        if constexpr (kLutBytes<T> > 0) {
+            // uint8: the vector's 16 bits are two table lookups (8 bits -> 8 bytes each) instead of sixteen ALU operations
 #pragma unroll 4
-        for (int v = wi * 32 + lane; v < v_end; v += nw * 32)
-            if (v >= v_begin) store_vec(vp + v, expand_bits<T>(bits[v / VW] >> ((v % VW) * VB)));
+            for (int v = wi * 32 + lane; v < v_end; v += nw * 32) {
+                if (v >= v_begin) {
+                    const uint32_t h = bits[v >> 1] >> ((v & 1) * 16);
+                    const uint2 lo = lut[h & 0xFFu], hi = lut[(h >> 8) & 0xFFu];
+                    store_vec(vp + v, make_uint4(lo.x, lo.y, hi.x, hi.y));
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int v = wi * 32 + lane; v < v_end; v += nw * 32)
+                if (v >= v_begin) store_vec(vp + v, expand_bits<T>(bits[v / VW] >> ((v % VW) * VB)));
+        }
     }
 }
 
@@ -375,7 +401,7 @@ __device__ __forceinline__ void stream_vectors(const uint32_t* __restrict__ bits
 // to other envs).
 template <typename T>
 __device__ __forceinline__ void stream_env(const uint32_t* __restrict__ bits, int nbits, T* __restrict__ out, int wi, int nw,
-                                           int lane) {
+                                           int lane, const uint2* __restrict__ lut) {
     constexpr int VB = kVecElems<T>;
     const int pad = obs_pad(out);
     const int total = pad + nbits;
@@ -386,7 +412,7 @@ __device__ __forceinline__ void stream_env(const uint32_t* __restrict__ bits, in
         const int t = max(v_end * VB, pad + head_n) + lane;         // first bit covered by neither head nor full vectors
         if (t < total) out[t - pad] = from_bit<T>((bits[t >> 5] >> (t & 31)) & 1u);
     }
-    stream_vectors<T>(bits, reinterpret_cast<uint4*>(out - pad), v_begin, v_end, wi, nw, lane);
+    stream_vectors<T>(bits, reinterpret_cast<uint4*>(out - pad), v_begin, v_end, wi, nw, lane, lut);
 }
 
 // Packed copy of the observation block for rollout storage: agent a's C*G*G bits start at word a*wpa
@@ -406,14 +432,21 @@ __device__ __forceinline__ void store_packed(const DevPlan& P, const uint32_t* _
 
 template <typename T>
 __device__ __forceinline__ void write_obs(const DevPlan& P, const Launch& L, const WarpMem& w, long long env, uint32_t me,
-                                          uint32_t rev_mask, int lane) {
+                                          uint32_t rev_mask, int lane, const uint2* __restrict__ lut) {
     if (!L.obs && !L.obs_bits) return;
     T* out = L.obs ? reinterpret_cast<T*>(L.obs) + env * (long long)P.E : nullptr;
     const int pad = out ? obs_pad(out) : 0;
     build_obs_bits(P, w, me, rev_mask, pad, lane);
     if (L.obs_bits) store_packed(P, w.bits, pad, L.obs_bits + env * (long long)(P.N * P.wpa), 0, 1, lane);
-    if (out) stream_env<T>(w.bits, P.E, out, 0, 1, lane);
+    if (out) stream_env<T>(w.bits, P.E, out, 0, 1, lane, lut);
 }
+
+// Element codes of the metadata block (host-built, DevPlan::meta_codes): what element (a, m) holds
+enum : unsigned { kMetaPct = 0, kMetaRatio0 = 1, kMetaRatio1 = 2, kMetaOne = 3, kMetaZero = 4, kMetaHp = 0x10, kMetaFlag = 0x20 };
+
+#ifndef CTF_META_VEC
+#define CTF_META_VEC 1   // 1: whole [N][M] block as float4 stores through the code table; 0: one 4-byte store per element and agent
+#endif
 
 __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int step, int caps0, int caps1,
                                            float* __restrict__ meta_env, int lane) {
@@ -428,6 +461,26 @@ __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int st
     const float quot = __half2float(__double2half((double)num / (double)den));
     const float pct = __shfl_sync(kFull, quot, 0);
     const float ratio0 = __shfl_sync(kFull, quot, 1), ratio1 = __shfl_sync(kFull, quot, 2);
+#if CTF_META_VEC
+    // The block's layout is static, so the host compiled it into one code per element; lane l of pass `it` produces
+    // elements 4k .. 4k+3 (k = 32 it + l) and stores them as one float4 (N*M is a multiple of 4 for every N).
+    const int n4 = (N * M) >> 2;
+    for (int it = 0; it * 32 < n4; ++it) {
+        const int k = it * 32 + lane;
+        const uint32_t codes = P.meta_codes[k & 63];
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = (codes >> (8 * j)) & 0xFFu;
+            const uint32_t sp = __shfl_sync(kFull, pair, c & 7u);
+            float x = c == kMetaPct ? pct : (c == kMetaRatio0 ? ratio0 : (c == kMetaRatio1 ? ratio1 : (c == kMetaOne ? 1.0f : 0.0f)));
+            if (c & kMetaHp) x = (float)(sp & 0xFFu);
+            if (c & kMetaFlag) x = (float)(sp >> 8);
+            v[j] = x;
+        }
+        if (k < n4) reinterpret_cast<float4*>(meta_env)[k] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+#else
     const int m = lane;                       // lane m produces element m of each agent's vector
     const int q4 = m >= 6 ? ((m - 6) >> 1) * 4 : 0;
     for (int a = 0; a < N; ++a) {
@@ -439,6 +492,7 @@ __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int st
         else v = m == 0 ? pct : (P.team[a] == 0 ? ratio0 : ratio1);
         if (m < M) meta_env[a * M + m] = v;
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,13 +518,13 @@ struct Deltas {
     uint32_t lo = 0, hi = 0;  // metrics 0..7, 8..12
 };
 
+// Every bump of one actor's turn is warp-uniform (same condition and amount in all lanes), so the turn's deltas are
+// summed in uniform registers and merged into the actor's lane once per turn.
 template <bool STATS>
-__device__ __forceinline__ void bump(Deltas& d, int metric, int agent, uint32_t by, int lane) {
+__device__ __forceinline__ void bump(Deltas& turn, int metric, uint32_t by) {
     if (STATS) {
-        if (lane == agent) {
-            if (metric < 8) d.lo += by << (4 * metric);
-            else d.hi += by << (4 * (metric - 8));
-        }
+        if (metric < 8) turn.lo += by << (4 * metric);
+        else turn.hi += by << (4 * (metric - 8));
     }
 }
 
@@ -480,10 +534,11 @@ __device__ __forceinline__ void bump(Deltas& d, int metric, int agent, uint32_t 
 template <typename T, bool STATS>
 __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L) {
     extern __shared__ uint4 smem_raw[];
+    const uint2* lut = init_expand_lut<T>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long env = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (env >= L.B) return;
-    const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw), warp);
+    const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T>, warp);
 
     if (lane < kGridBytes / 16)
         reinterpret_cast<uint4*>(w.grid)[lane] = reinterpret_cast<const uint4*>(P.grid_template)[lane];
@@ -508,7 +563,7 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ DevP
     const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
                                                         : __ballot_sync(kFull, lane < P.N && P.obs_rev[li]);
     if (L.meta) write_meta(P, me, 0, 0, 0, L.meta + env * (long long)P.N * P.M, lane);
-    write_obs<T>(P, L, w, env, me, rev_mask, lane);
+    write_obs<T>(P, L, w, env, me, rev_mask, lane, lut);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -517,10 +572,11 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ DevP
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_observe(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L) {
     extern __shared__ uint4 smem_raw[];
+    const uint2* lut = init_expand_lut<T>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long env = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (env >= L.B) return;
-    const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw), warp);
+    const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T>, warp);
     if (lane < kGridBytes / 16)
         reinterpret_cast<uint4*>(w.grid)[lane] = ld_state(reinterpret_cast<const uint4*>(L.grid + env * kGridBytes) + lane);
     const int li = lane & 7;
@@ -534,7 +590,7 @@ __global__ void __launch_bounds__(kThreads) k_observe(const __grid_constant__ De
     const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
                                                         : __ballot_sync(kFull, lane < P.N && P.obs_rev[li]);
     if (L.meta) write_meta(P, me, (int)ev.x, (int)ev.z, (int)ev.w, L.meta + env * (long long)P.N * P.M, lane);
-    write_obs<T>(P, L, w, env, me, rev_mask, lane);
+    write_obs<T>(P, L, w, env, me, rev_mask, lane, lut);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -608,6 +664,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
         int ar = ag_r(am), ac = ag_c(am), aflag = ag_flag(am), ahp = ag_hp(am);
         int ainv = (type == 3) ? __shfl_sync(kFull, inv, a) : 0;
         bool cap_now = false;
+        Deltas turn;                                           // this turn's counter increments (warp-uniform)
 
         // ---------------- act (:700-732)
         const int nr = ar + P.delta[type][act_code][0], nc = ac + P.delta[type][act_code][1];
@@ -627,7 +684,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
                     __syncwarp();
                     w.grid[ofr * kRow + ofc] = 1;
                     __syncwarp();
-                    bump<STATS>(dl, CTF_M_FLAG_PICKUPS, a, 1, lane);
+                    bump<STATS>(turn, CTF_M_FLAG_PICKUPS, 1);
                 }
                 if (cheb(nr, nc, hfr, hfc) <= 1 && aflag == 1 &&
                     (!P.home_flag_capture || w.grid[hfr * kRow + hfc] == P.flag_tile[team])) {        // capture (:594-610)
@@ -638,7 +695,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
                     if (team == 0) caps0 += 1; else caps1 += 1;
                     cap_team |= 1u << team;
                     cap_now = true;
-                    bump<STATS>(dl, CTF_M_FLAG_CAPTURES, a, 1, lane);
+                    bump<STATS>(turn, CTF_M_FLAG_CAPTURES, 1);
                 }
                 if (act_code >= 5 && type == 2) ahp -= P.vault_cost_q;                               // (:652-657)
             } else if (act_code >= 5 && type == 3 && ainv > 0 && target == 0 &&
@@ -650,11 +707,9 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
                 __syncwarp();
                 ainv -= 1;
                 if (STATS) {
-                    bump<STATS>(dl, CTF_M_BLOCKS_LAID, a, 1, lane);
-                    bump<STATS>(dl, CTF_M_BLOCKS_LAID_DIST_OWN_FLAG, a,
-                                (uint32_t)cheb(ar, ac, P.capture_pos[team][0], P.capture_pos[team][1]), lane);
-                    bump<STATS>(dl, CTF_M_BLOCKS_LAID_DIST_OPP_FLAG, a,
-                                (uint32_t)cheb(ar, ac, P.capture_pos[1 - team][0], P.capture_pos[1 - team][1]), lane);
+                    bump<STATS>(turn, CTF_M_BLOCKS_LAID, 1);
+                    bump<STATS>(turn, CTF_M_BLOCKS_LAID_DIST_OWN_FLAG, (uint32_t)cheb(ar, ac, P.capture_pos[team][0], P.capture_pos[team][1]));
+                    bump<STATS>(turn, CTF_M_BLOCKS_LAID_DIST_OPP_FLAG, (uint32_t)cheb(ar, ac, P.capture_pos[1 - team][0], P.capture_pos[1 - team][1]));
                 }
             } else if (act_code < 5 && type == 3 && (target == 2 || target == 3)) {
                 // mine_block (:677-690)
@@ -663,7 +718,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
                 __syncwarp();
                 if (target == 3) {
                     if (ainv < P.max_agent_blocks) ainv += P.block_pickup_value;
-                    bump<STATS>(dl, CTF_M_BLOCKS_MINED, a, 1, lane);
+                    bump<STATS>(turn, CTF_M_BLOCKS_MINED, 1);
                 }
             }
         }
@@ -673,6 +728,11 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
             captured = cap_now;
         }
 
+        // distance of this lane's agent to the actor after its move: tag range now, adjacency metrics below
+        // (recomputed there only if a respawn moved somebody in between)
+        const int d_me = cheb(ar, ac, ag_r(me), ag_c(me));
+        bool moved_by_respawn = false;
+
         // ---------------- tagging_logic (:796-837)
         if (P.damage_q[type] > 0) {
             const int dmg = (type == 1 && cheb(ar, ac, P.flag_pos[team][0], P.flag_pos[team][1]) <= P.guardian_distance)
@@ -681,15 +741,15 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
             const int site = 4 * a + (my_slot < 0 ? 0 : my_slot);
             const uint32_t roll = __shfl_sync(kFull, wd[0], site);
             const uint32_t pick_word = __shfl_sync(kFull, wd[1], site);
-            const bool hit = is_opp && (unsigned long long)roll < P.tag_threshold &&
-                             cheb(ar, ac, ag_r(me), ag_c(me)) <= P.tagging_range;
+            const bool hit = is_opp && (unsigned long long)roll < P.tag_threshold && d_me <= P.tagging_range;
             int hp = ag_hp(me);
             if (hit) hp -= dmg;                                                                      // (:818)
             const bool lethal = hit && hp <= 0;                                                      // (:824)
             if (hit) me = (me & 0xFFFFu) | ((uint32_t)(hp & 0xFFFF) << 16);
             const unsigned hits = __ballot_sync(kFull, hit);
             unsigned deaths = __ballot_sync(kFull, lethal);
-            if (STATS && hits) bump<STATS>(dl, CTF_M_TAG_COUNT, a, (uint32_t)__popc(hits), lane);
+            moved_by_respawn = deaths != 0;
+            if (STATS && hits) bump<STATS>(turn, CTF_M_TAG_COUNT, (uint32_t)__popc(hits));
             // lethal hits respawn one after the other in opponent-id order: each changes the next one's window
             while (deaths) {
                 const int opp = __ffs(deaths) - 1;
@@ -697,7 +757,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
                 const uint32_t om = __shfl_sync(kFull, me, opp);
                 const uint32_t ow = __shfl_sync(kFull, pick_word, opp);
                 const int oteam = 1 - team;
-                if (ag_flag(om)) bump<STATS>(dl, CTF_M_FLAG_DISPOSSESSIONS, a, 1, lane);
+                if (ag_flag(om)) bump<STATS>(turn, CTF_M_FLAG_DISPOSSESSIONS, 1);
                 // respawn (:761-794): open cells of the clipped 3x3 window around the victim's spawn, row-major
                 const int x = P.spawn_pos[oteam][0], y = P.spawn_pos[oteam][1];
                 const int wr = x - 1 + lane / 3, wc = y - 1 + lane % 3;
@@ -722,7 +782,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
                     atomicOr(L.faults, CTF_FAULT_RESPAWN_BLOCKED);   // randint(0) raises in the reference (:771)
                 }
                 if (lane == a) tag_reward = true;
-                bump<STATS>(dl, CTF_M_RESPAWN_TAG_COUNT, a, 1, lane);
+                bump<STATS>(turn, CTF_M_RESPAWN_TAG_COUNT, 1);
             }
         }
 
@@ -730,13 +790,15 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
         if (STATS) {
             const int d_own = cheb(ar, ac, P.capture_pos[team][0], P.capture_pos[team][1]);
             const int d_opp = cheb(ar, ac, P.capture_pos[1 - team][0], P.capture_pos[1 - team][1]);
-            if (d_own <= P.zone_distance) bump<STATS>(dl, CTF_M_STEPS_DEFENDING_ZONE, a, 1, lane);
-            if (d_opp <= P.zone_distance) bump<STATS>(dl, CTF_M_STEPS_ATTACKING_ZONE, a, 1, lane);
-            const bool near = lane < N && my_slot >= 0 && cheb(ar, ac, ag_r(me), ag_c(me)) <= 1;
+            if (d_own <= P.zone_distance) bump<STATS>(turn, CTF_M_STEPS_DEFENDING_ZONE, 1);
+            if (d_opp <= P.zone_distance) bump<STATS>(turn, CTF_M_STEPS_ATTACKING_ZONE, 1);
+            const int d_now = moved_by_respawn ? cheb(ar, ac, ag_r(me), ag_c(me)) : d_me;
+            const bool near = lane < N && my_slot >= 0 && d_now <= 1;
             const unsigned mates = __ballot_sync(kFull, near && my_team == team);   // includes the agent itself
             const unsigned opps = __ballot_sync(kFull, near && my_team != team);
-            if (mates) bump<STATS>(dl, CTF_M_STEPS_ADJ_TEAMMATE, a, (uint32_t)__popc(mates), lane);
-            if (opps) bump<STATS>(dl, CTF_M_STEPS_ADJ_OPPONENT, a, (uint32_t)__popc(opps), lane);
+            if (mates) bump<STATS>(turn, CTF_M_STEPS_ADJ_TEAMMATE, (uint32_t)__popc(mates));
+            if (opps) bump<STATS>(turn, CTF_M_STEPS_ADJ_OPPONENT, (uint32_t)__popc(opps));
+            if (lane == a) { dl.lo += turn.lo; dl.hi += turn.hi; }
         }
     }
 
@@ -803,13 +865,14 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
 template <typename T, bool STATS>
 __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L) {
     extern __shared__ uint4 smem_raw[];
+    const uint2* lut = init_expand_lut<T>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long env = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (env >= L.B) return;
-    const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw), warp);
+    const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T>, warp);
     uint32_t rev_mask;
     const uint32_t me = step_env<STATS>(P, L, w, env, lane, rev_mask);
-    write_obs<T>(P, L, w, env, me, rev_mask, lane);   // observations straight into the policy's input buffers
+    write_obs<T>(P, L, w, env, me, rev_mask, lane, lut);   // observations straight into the policy's input buffers
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -854,8 +917,9 @@ template <typename T, bool STATS>
 __global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L,
                                                      int n_logic, int n_stream, unsigned int* __restrict__ ctr) {
     extern __shared__ uint4 smem_raw[];
-    WsCtl* c = reinterpret_cast<WsCtl*>(smem_raw);
-    unsigned char* warp_base = reinterpret_cast<unsigned char*>(smem_raw) + kWsCtlBytes;
+    const uint2* lut = init_expand_lut<T>(smem_raw);
+    WsCtl* c = reinterpret_cast<WsCtl*>(reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T>);
+    unsigned char* warp_base = reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T> + kWsCtlBytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { c->tail = 0; c->producers = n_logic; }
     if (threadIdx.x < kWsQ) { c->ready[threadIdx.x] = 0; c->done[threadIdx.x] = 0; }
@@ -928,7 +992,7 @@ __global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ Dev
             const uint32_t* bits = warp_mem(P, warp_base, buf).bits;
             T* out = L.obs ? reinterpret_cast<T*>(L.obs) + env * (long long)P.E : nullptr;
             if (L.obs_bits) store_packed(P, bits, out ? obs_pad(out) : 0, L.obs_bits + env * (long long)(P.N * P.wpa), wi, n_stream, lane);
-            if (out) stream_env<T>(bits, P.E, out, wi, n_stream, lane);
+            if (out) stream_env<T>(bits, P.E, out, wi, n_stream, lane, lut);
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
@@ -959,7 +1023,8 @@ template <typename T>
 __global__ void __launch_bounds__(kUnpackThreads) k_unpack(const uint32_t* __restrict__ packed, T* __restrict__ out,
                                                           long long n_blocks, int nbits, int wpa, int chunk, int bits_words) {
     extern __shared__ uint4 smem_raw[];
-    uint32_t* bits = reinterpret_cast<uint32_t*>(smem_raw);   // [bits_words]
+    const uint2* lut = init_expand_lut<T>(smem_raw);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T>);   // [bits_words]
     uint32_t* pk = bits + bits_words;                          // [chunk * wpa]
     const long long blk0 = (long long)blockIdx.x * chunk;
     const int nb = (int)min((long long)chunk, n_blocks - blk0);
@@ -984,7 +1049,7 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack(const uint32_t* __res
         bits[wd] = val;
     }
     __syncthreads();
-    stream_env<T>(bits, total, dst, threadIdx.x >> 5, kUnpackThreads / 32, threadIdx.x & 31);
+    stream_env<T>(bits, total, dst, threadIdx.x >> 5, kUnpackThreads / 32, threadIdx.x & 31, lut);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1025,6 +1090,7 @@ struct ctf_env {
     unsigned int* ws_ctr;    // device [2]: next env id, logic warps that have finished; re-armed by the kernel itself
     int ws_logic, ws_stream, ws_ctas;   // logic / stream warps per CTA, CTAs in the grid
     long long ws_min_envs;   // batches below this use the warp-per-env kernel
+    int n_sm;
     size_t ws_smem_bytes;
 };
 
@@ -1078,6 +1144,15 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
     P.bits_words = (((P.E + 128 + 31) / 32 + 1) + 15) / 16 * 16;  // pad (<= 127 bits) + 1 slack word, whole 16-word groups
     P.wpa = (c.n_channels * G * G + 31) / 32;
     P.game_steps = c.game_steps; P.flip_axis = c.flip_axis;
+    {   // out[i][j] = in[fr][fc] with (fr, fc) = (G1-r, G1-c) both axes, (G1-r, c) rows, (r, G1-c) columns, (G1-c, G1-r) anti-diagonal
+        const int G1 = G - 1;
+        switch (c.flip_axis) {
+            case -1: P.flip_a = -G; P.flip_b = -1; P.flip_d = G1 * G + G1; break;
+            case 0: P.flip_a = -G; P.flip_b = 1; P.flip_d = G1 * G; break;
+            case 1: P.flip_a = G; P.flip_b = -1; P.flip_d = G1; break;
+            default: P.flip_a = -1; P.flip_b = -G; P.flip_d = G1 * G + G1; break;
+        }
+    }
     P.use_adjusted_rewards = c.use_adjusted_rewards; P.home_flag_capture = c.home_flag_capture;
     P.drop_flag_when_no_hp = c.drop_flag_when_no_hp; P.reverse_team1_actions = c.reverse_team1_actions;
     P.heal_q = c.heal_q; P.vault_cost_q = c.vault_cost_q; P.vault_min_q = c.vault_min_q;
@@ -1137,6 +1212,25 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
             if (q < N) put(c.opponents[team][j]);
         P.meta_row[a] = row;
     }
+    // the same layout as one code per element (write_meta's float4 path)
+    {
+        unsigned char codes[256];
+        memset(codes, kMetaZero, sizeof(codes));
+        const int M = 6 + 2 * N;
+        for (int a = 0; a < N; ++a) {
+            unsigned char* row = codes + a * M;
+            row[0] = kMetaPct;
+            row[1] = c.agent_team[a] == 0 ? kMetaRatio0 : kMetaRatio1;
+            for (int t = 0; t < 4; ++t) row[2 + t] = (t == c.agent_type[a]) ? kMetaOne : kMetaZero;
+            for (int q = 0; q < N; ++q) {
+                const unsigned srcAgent = (P.meta_row[a] >> (4 * q)) & 15u;
+                row[6 + 2 * q] = srcAgent == 15u ? kMetaZero : (unsigned char)(kMetaHp | srcAgent);
+                row[7 + 2 * q] = srcAgent == 15u ? kMetaZero : (unsigned char)(kMetaFlag | srcAgent);
+            }
+        }
+        for (int k = 0; k < 64; ++k)
+            P.meta_codes[k] = codes[4 * k] | (codes[4 * k + 1] << 8) | (codes[4 * k + 2] << 16) | ((unsigned)codes[4 * k + 3] << 24);
+    }
     for (int r = 0; r < G; ++r)
         for (int cc = 0; cc < G; ++cc) {
             const uint8_t t = c.grid_template[r * G + cc];
@@ -1170,7 +1264,8 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
     if (rc != CTF_OK) { delete h; return rc; }
     h->cfg = *cfg; h->B = num_envs; h->device = device; h->stats_level = stats_level; h->obs_dtype = obs_dtype;
     h->seed = seed; h->env_id_base = env_id_base;
-    h->smem_bytes = (size_t)h->plan.warp_smem_bytes * kWarpsPerCta;
+    const size_t lut_bytes = (CTF_U8_LUT && obs_dtype == CTF_OBS_U8) ? 2048 : 0;   // kLutBytes<uint8_t>
+    h->smem_bytes = lut_bytes + (size_t)h->plan.warp_smem_bytes * kWarpsPerCta;
     h->faults = nullptr; h->actions_stage = nullptr; h->rewards_stage = nullptr; h->dones_stage = nullptr;
     DeviceGuard guard(device);
     cudaError_t e = guard.err;
@@ -1198,8 +1293,9 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
         delete h;
         return fail(CTF_ERR_INVALID, "CTF_WS_LOGIC / CTF_WS_STREAM / CTF_WS_CTAS_PER_SM out of range");
     }
+    h->n_sm = n_sm;
     h->ws_ctas = n_sm * ctas_per_sm;
-    h->ws_smem_bytes = (size_t)kWsCtlBytes + (size_t)h->plan.warp_smem_bytes * h->ws_logic;
+    h->ws_smem_bytes = lut_bytes + (size_t)kWsCtlBytes + (size_t)h->plan.warp_smem_bytes * h->ws_logic;
     // below ~4 envs per logic warp the persistent kernel is all ramp-up and tail: use the warp-per-env kernel
     h->ws_min_envs = (long long)env_int("CTF_WS_MIN_ENVS", 4 * h->ws_ctas * h->ws_logic);
     const size_t obs_bytes_per_agent = (size_t)h->plan.C * h->plan.GG * (obs_dtype == CTF_OBS_F32 ? 4 : (obs_dtype == CTF_OBS_U8 ? 1 : 2));
@@ -1261,6 +1357,7 @@ static int make_launch(ctf_handle_t h, const ctf_state_t& st, const ctf_outputs_
     if ((reinterpret_cast<uintptr_t>(st.grid) & 15) || (reinterpret_cast<uintptr_t>(st.envs) & 15) ||
         (reinterpret_cast<uintptr_t>(st.agents) & 7))
         return fail(CTF_ERR_INVALID, "state buffers must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(out.meta) & 15) return fail(CTF_ERR_INVALID, "outputs.meta must be 16-byte aligned");
     memset(&L, 0, sizeof(L));
     L.grid = st.grid; L.agents = reinterpret_cast<unsigned long long*>(st.agents); L.envs = reinterpret_cast<uint4*>(st.envs);
     L.stats = h->stats_level > 0 ? st.stats : nullptr;
@@ -1372,7 +1469,7 @@ extern "C" int ctf_unpack_obs(ctf_handle_t h, const uint32_t* packed, void* out,
     while (chunk > 1 && ((size_t)(chunk * nbits) / 8 + (size_t)chunk * wpa * 4) > 40 * 1024) --chunk;   // static shared-memory budget
     const int bits_words = (((chunk * nbits + 128 + 31) / 32 + 1) + 15) / 16 * 16;
     const unsigned grid = (unsigned)((n_agent_blocks + chunk - 1) / chunk);
-    const size_t smem = ((size_t)bits_words + (size_t)chunk * wpa) * sizeof(uint32_t);
+    const size_t smem = ((size_t)bits_words + (size_t)chunk * wpa) * sizeof(uint32_t) + ((CTF_U8_LUT && out_dtype == CTF_OBS_U8) ? 2048 : 0);
     with_obs_type(out_dtype, [&](auto tag) {
         using T = decltype(tag);
         k_unpack<T><<<grid, kUnpackThreads, smem, s>>>(packed, static_cast<T*>(out), n_agent_blocks, nbits, wpa, chunk, bits_words);
