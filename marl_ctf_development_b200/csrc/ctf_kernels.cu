@@ -441,56 +441,49 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const Launch& L, con
     if (out) stream_env<T>(w.bits, P.E, out, 0, 1, lane, lut);
 }
 
-// Element codes of the metadata block (host-built, DevPlan::meta_codes): what element (a, m) holds
-enum : unsigned { kMetaPct = 0, kMetaRatio0 = 1, kMetaRatio1 = 2, kMetaOne = 3, kMetaZero = 4, kMetaHp = 0x10, kMetaFlag = 0x20 };
-
 #ifndef CTF_META_VEC
-#define CTF_META_VEC 1   // 1: whole [N][M] block as float4 stores through the code table; 0: one 4-byte store per element and agent
+#define CTF_META_VEC 1   // 1: whole [N][M] block as float4 stores; 0: one 4-byte store per element
 #endif
+// Element codes of the metadata block (host-built, DevPlan::meta_codes): the LANE whose value the element takes.
+// write_meta spreads the block's distinct values over the warp — lane i < 8: hp8 of agent i, lane 8 + i: has_flag of
+// agent i, lanes 16 / 17 / 18: game progress and the two capture ratios, lane 19: 1.0, lane 20: 0.0 — so that every
+// element is one shuffle.
+enum : unsigned { kMetaHp = 0, kMetaFlag = 8, kMetaPct = 16, kMetaRatio0 = 17, kMetaRatio1 = 18, kMetaOne = 19, kMetaZero = 20 };
 
 __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int step, int caps0, int caps1,
                                            float* __restrict__ meta_env, int lane) {
     const int N = P.N, M = P.M;
     const int li = lane & 7;
-    // hp8[i] = uint8(agent_hp[TYPE_i as agent id] / AGENT_TYPE_HP[TYPE_i])  (:1039-1041); lane i keeps hp8 | has_flag<<8
+    // hp8[i] = uint8(agent_hp[TYPE_i as agent id] / AGENT_TYPE_HP[TYPE_i])  (:1039-1041)
     const uint32_t src = __shfl_sync(kFull, me, P.meta_hp_src[li]);
-    const uint32_t pair = (uint32_t)((ag_hp(src) / P.hp_max_q[P.type[li]]) & 0xFF) | ((uint32_t)ag_flag(me) << 8);
-    // the three fp64 quotients that go through float16 (:1035-1036, :1044), one per lane, in a single pass
-    const int num = lane == 0 ? step : (lane == 1 ? caps0 + 1 : caps1 + 1);
-    const int den = lane == 0 ? P.game_steps : (lane == 1 ? caps1 + 1 : caps0 + 1);
+    const uint32_t mine = __shfl_sync(kFull, me, li);
+    const float hp8 = (float)((ag_hp(src) / P.hp_max_q[P.type[li]]) & 0xFF);
+    // the three fp64 quotients that go through float16 (:1035-1036, :1044), one per lane 16..18, in a single pass
+    const int num = lane == 16 ? step : (lane == 17 ? caps0 + 1 : caps1 + 1);
+    const int den = lane == 16 ? P.game_steps : (lane == 17 ? caps1 + 1 : caps0 + 1);
     const float quot = __half2float(__double2half((double)num / (double)den));
-    const float pct = __shfl_sync(kFull, quot, 0);
-    const float ratio0 = __shfl_sync(kFull, quot, 1), ratio1 = __shfl_sync(kFull, quot, 2);
+    const float val = lane < 8 ? hp8 : (lane < 16 ? (float)ag_flag(mine) : (lane < 19 ? quot : (lane == 19 ? 1.0f : 0.0f)));
 #if CTF_META_VEC
-    // The block's layout is static, so the host compiled it into one code per element; lane l of pass `it` produces
-    // elements 4k .. 4k+3 (k = 32 it + l) and stores them as one float4 (N*M is a multiple of 4 for every N).
+    // The block's layout is static, so the host compiled it into one source lane per element; lane l of pass `it`
+    // produces elements 4k .. 4k+3 (k = 32 it + l) and stores them as one float4 (N*M is a multiple of 4 for every N).
     const int n4 = (N * M) >> 2;
     for (int it = 0; it * 32 < n4; ++it) {
         const int k = it * 32 + lane;
         const uint32_t codes = P.meta_codes[k & 63];
-        float v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t c = (codes >> (8 * j)) & 0xFFu;
-            const uint32_t sp = __shfl_sync(kFull, pair, c & 7u);
-            float x = c == kMetaPct ? pct : (c == kMetaRatio0 ? ratio0 : (c == kMetaRatio1 ? ratio1 : (c == kMetaOne ? 1.0f : 0.0f)));
-            if (c & kMetaHp) x = (float)(sp & 0xFFu);
-            if (c & kMetaFlag) x = (float)(sp >> 8);
-            v[j] = x;
-        }
-        if (k < n4) reinterpret_cast<float4*>(meta_env)[k] = make_float4(v[0], v[1], v[2], v[3]);
+        float4 v;
+        v.x = __shfl_sync(kFull, val, codes & 31u);
+        v.y = __shfl_sync(kFull, val, (codes >> 8) & 31u);
+        v.z = __shfl_sync(kFull, val, (codes >> 16) & 31u);
+        v.w = __shfl_sync(kFull, val, (codes >> 24) & 31u);
+        if (k < n4) reinterpret_cast<float4*>(meta_env)[k] = v;
     }
 #else
-    const int m = lane;                       // lane m produces element m of each agent's vector
-    const int q4 = m >= 6 ? ((m - 6) >> 1) * 4 : 0;
-    for (int a = 0; a < N; ++a) {
-        const uint32_t srcAgent = (P.meta_row[a] >> q4) & 15u;
-        const uint32_t sp = __shfl_sync(kFull, pair, srcAgent & 7u);
-        float v;
-        if (m >= 6) v = srcAgent == 15u ? 0.0f : (float)((m & 1) ? (sp >> 8) : (sp & 0xFFu));
-        else if (m >= 2) v = (m - 2 == P.type[a]) ? 1.0f : 0.0f;
-        else v = m == 0 ? pct : (P.team[a] == 0 ? ratio0 : ratio1);
-        if (m < M) meta_env[a * M + m] = v;
+    const int total = N * M;                  // one 4-byte store per element
+    for (int e0 = 0; e0 < total; e0 += 32) {
+        const int e = e0 + lane;
+        const uint32_t code = (P.meta_codes[(e >> 2) & 63] >> (8 * (e & 3))) & 31u;
+        const float x = __shfl_sync(kFull, val, code);
+        if (e < total) meta_env[e] = x;
     }
 #endif
 }
@@ -651,6 +644,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
     }
     __syncwarp();
 
+    uint32_t turn_pos = 0;      // this lane's agent's position at the end of its own turn (zonal metrics)
     bool captured = false;      // this lane's agent captured during its own act (:728-730)
     bool tag_reward = false;    // this lane's agent made a lethal tag (:832)
     uint32_t cap_team = 0;      // _flag_capture_team_current_move as bits (:858)
@@ -786,12 +780,10 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
             }
         }
 
-        // ---------------- zonal / proximity metrics (:879-902)
+        // ---------------- proximity metrics (:890-902); the zonal ones (:879-889) only need the actor's position at
+        // its own turn, which lane a keeps in turn_pos: they are evaluated for all agents at once after the loop
         if (STATS) {
-            const int d_own = cheb(ar, ac, P.capture_pos[team][0], P.capture_pos[team][1]);
-            const int d_opp = cheb(ar, ac, P.capture_pos[1 - team][0], P.capture_pos[1 - team][1]);
-            if (d_own <= P.zone_distance) bump<STATS>(turn, CTF_M_STEPS_DEFENDING_ZONE, 1);
-            if (d_opp <= P.zone_distance) bump<STATS>(turn, CTF_M_STEPS_ATTACKING_ZONE, 1);
+            if (lane == a) turn_pos = (uint32_t)ar | ((uint32_t)ac << 4);
             const int d_now = moved_by_respawn ? cheb(ar, ac, ag_r(me), ag_c(me)) : d_me;
             const bool near = lane < N && my_slot >= 0 && d_now <= 1;
             const unsigned mates = __ballot_sync(kFull, near && my_team == team);   // includes the agent itself
@@ -802,6 +794,14 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
         }
     }
 
+    // ---- zonal metrics (:879-889) of every agent, at the position it had at its own turn
+    if (STATS) {
+        const int tr = (int)(turn_pos & 15u), tc = (int)(turn_pos >> 4);
+        const int d_own = cheb(tr, tc, P.capture_pos[my_team][0], P.capture_pos[my_team][1]);
+        const int d_opp = cheb(tr, tc, P.capture_pos[1 - my_team][0], P.capture_pos[1 - my_team][1]);
+        dl.hi += ((d_own <= P.zone_distance ? 1u : 0u) << (4 * (CTF_M_STEPS_DEFENDING_ZONE - 8))) +
+                 ((d_opp <= P.zone_distance ? 1u : 0u) << (4 * (CTF_M_STEPS_ATTACKING_ZONE - 8)));
+    }
     // ---- heal_agents (:839-847)
     {
         const int mx = P.hp_max_q[my_type];
@@ -1224,8 +1224,8 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
             for (int t = 0; t < 4; ++t) row[2 + t] = (t == c.agent_type[a]) ? kMetaOne : kMetaZero;
             for (int q = 0; q < N; ++q) {
                 const unsigned srcAgent = (P.meta_row[a] >> (4 * q)) & 15u;
-                row[6 + 2 * q] = srcAgent == 15u ? kMetaZero : (unsigned char)(kMetaHp | srcAgent);
-                row[7 + 2 * q] = srcAgent == 15u ? kMetaZero : (unsigned char)(kMetaFlag | srcAgent);
+                row[6 + 2 * q] = srcAgent == 15u ? kMetaZero : (unsigned char)(kMetaHp + srcAgent);
+                row[7 + 2 * q] = srcAgent == 15u ? kMetaZero : (unsigned char)(kMetaFlag + srcAgent);
             }
         }
         for (int k = 0; k < 64; ++k)
