@@ -861,7 +861,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
 }
 
 // Warp-per-env step kernel: every warp steps its env and then streams that env's observation block itself.
-// Used for small batches (under a few waves of the persistent kernel below) and as the A/B baseline.
+// The default kernel of ctf_step.
 template <typename T, bool STATS>
 __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L) {
     extern __shared__ uint4 smem_raw[];
@@ -876,7 +876,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent, warp-specialised step kernel (the hot kernel at large B)
+// Persistent, warp-specialised step kernel (opt-in: CTF_WS=1)
 // ------------------------------------------------------------------------------------------------
 // What bounds the step is the 100 KB-per-env observation write, and HBM takes that stream fastest when few env
 // blocks are open at a time and they are visited in address order (profiles/r02_write_span_microbench.log: 0.88 ms
@@ -1277,15 +1277,16 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
     h->ws_ctr = nullptr;
     if (e == cudaSuccess) e = cudaMalloc(&h->ws_ctr, 128);   // two 32-bit counters (+ the profiling build's cycle totals)
     if (e == cudaSuccess) e = cudaMemset(h->ws_ctr, 0, 128);
-    // Shape of the persistent kernel: one CTA per SM with 8 logic + 12 stream warps unless overridden (A/B runs,
-    // tools/ws_sweep.py).  It beats the warp-per-env kernel only where the observation stream dwarfs the env logic —
-    // float32 8_arena-sized blocks (>= 12 KB per agent): 0.989 vs 1.003 ms at B = 65536, 0.264 vs 0.269 ms at 16384 —
-    // and loses where the logic is a larger share (7_gridlocked 0.73 vs 0.55 ms, uint8 / bf16 / packed-only outputs):
-    // profiles/r02_ws_matrix.log, r02_ab_pad.log.  CTF_WS=1 / 0 forces it on / off.
+    // The persistent kernel is opt-in (CTF_WS=1; shape: one CTA per SM with 8 logic + 16 stream warps unless overridden,
+    // tools/ws_sweep.py).  It only ever beat the warp-per-env kernel where the observation stream dwarfs the env logic —
+    // float32 8_arena-sized blocks: 0.989 vs 1.002 ms at B = 65536 when it was written, 0.996 vs 1.001 ms after the env
+    // logic was trimmed (profiles/r02_ws_final_sweep.jsonl) — and loses everywhere else (7_gridlocked 0.73 vs 0.55 ms,
+    // uint8 / bf16 / packed-only outputs: profiles/r02_ws_matrix.log).  Half a per cent does not pay for a second hot
+    // kernel, so ctf_step launches k_step unless asked otherwise; both pass the whole parity suite.
     int n_sm = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     h->ws_logic = env_int("CTF_WS_LOGIC", 8);
-    h->ws_stream = env_int("CTF_WS_STREAM", 12);
+    h->ws_stream = env_int("CTF_WS_STREAM", 16);
     const int ctas_per_sm = env_int("CTF_WS_CTAS_PER_SM", 1);
     if (h->ws_logic < 1 || h->ws_logic > kWsQ || h->ws_stream < 1 || (h->ws_logic + h->ws_stream) > 32 || ctas_per_sm < 1 ||
         ctas_per_sm > 4) {
@@ -1298,9 +1299,7 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
     h->ws_smem_bytes = lut_bytes + (size_t)kWsCtlBytes + (size_t)h->plan.warp_smem_bytes * h->ws_logic;
     // below ~4 envs per logic warp the persistent kernel is all ramp-up and tail: use the warp-per-env kernel
     h->ws_min_envs = (long long)env_int("CTF_WS_MIN_ENVS", 4 * h->ws_ctas * h->ws_logic);
-    const size_t obs_bytes_per_agent = (size_t)h->plan.C * h->plan.GG * (obs_dtype == CTF_OBS_F32 ? 4 : (obs_dtype == CTF_OBS_U8 ? 1 : 2));
-    const int ws_mode = env_int("CTF_WS", -1);   // -1: by the heuristic above
-    if (ws_mode == 0 || (ws_mode < 0 && obs_bytes_per_agent < 12000) || num_envs > 0x7FFFFFFFll) h->ws_min_envs = 0x7FFFFFFFFFFFFFFFll;
+    if (env_int("CTF_WS", 0) != 1 || num_envs > 0x7FFFFFFFll) h->ws_min_envs = 0x7FFFFFFFFFFFFFFFll;
     const int smem = (int)h->smem_bytes;
     const int ws_smem = (int)h->ws_smem_bytes;
 #define CTF_SET_SMEM(K, BYTES) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)

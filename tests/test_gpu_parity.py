@@ -614,7 +614,7 @@ def test_soak_every_experiment_full_episode_with_visits(exp):
 # ---------------------------------------------------------------------------------------------------
 @pytest.fixture
 def force_persistent_kernel(monkeypatch):
-    """ctf_create reads these: every batch size and output type then runs k_step_ws (default: large float32 batches)."""
+    """ctf_create reads these: every batch size and output type then runs k_step_ws (default: never)."""
     monkeypatch.setenv("CTF_WS", "1")
     monkeypatch.setenv("CTF_WS_MIN_ENVS", "1")
 
@@ -633,25 +633,21 @@ def test_persistent_kernel_against_oracle(force_persistent_kernel, exp, B, dtype
     assert info.ctas >= 1 and info.logic_warps + info.stream_warps <= 32
 
 
-def test_persistent_kernel_is_the_default_only_for_large_float32_blocks(monkeypatch):
+def test_persistent_kernel_is_opt_in_and_gives_identical_results(monkeypatch):
     for k in ("CTF_WS", "CTF_WS_MIN_ENVS"):
         monkeypatch.delenv(k, raising=False)
-    assert not _env("8_arena", 64).uses_persistent_kernel                      # too few envs
-    assert not _env("0_the_split", 20000).uses_persistent_kernel               # small observation blocks: logic-bound
-    assert not _env("8_arena", 20000, obs_dtype=torch.uint8).uses_persistent_kernel
+    plain = _env("8_arena", 20000)
+    assert not plain.uses_persistent_kernel                                    # default: the warp-per-env kernel
+    monkeypatch.setenv("CTF_WS", "1")
+    assert not _env("8_arena", 64).uses_persistent_kernel                      # under ~4 envs per logic warp: never
     big = _env("8_arena", 20000)
     assert big.uses_persistent_kernel
-    small = _env("8_arena", 20000)
-    monkeypatch.setenv("CTF_WS", "0")
-    other = _env("8_arena", 20000)
-    assert not other.uses_persistent_kernel
     acts = torch.randint(0, 9, (6, 20000, 8), dtype=torch.uint8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
     for t in range(6):
         big.step(acts[t])
-        other.step(acts[t])
-    assert torch.equal(big.obs, other.obs) and torch.equal(big.meta, other.meta) and torch.equal(big.rewards, other.rewards)
-    assert torch.equal(big._grid, other._grid) and torch.equal(big._agents, other._agents)
-    del small
+        plain.step(acts[t])
+    assert torch.equal(big.obs, plain.obs) and torch.equal(big.meta, plain.meta) and torch.equal(big.rewards, plain.rewards)
+    assert torch.equal(big._grid, plain._grid) and torch.equal(big._agents, plain._agents)
 
 
 def test_persistent_kernel_packed_outputs_and_graph_replay(force_persistent_kernel):
