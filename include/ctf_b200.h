@@ -243,6 +243,8 @@ int ctf_step_host(ctf_handle_t h, ctf_state_t state, const uint8_t* actions_host
 typedef struct ctf_kernel_info {
     int persistent, logic_warps, stream_warps, ctas;
     int64_t min_envs_for_persistent;
+    int warp_per_env_ctas_per_sm; /* resident-CTA cap of k_step / k_reset / k_observe (0: as many as fit) */
+    int reserved;
 } ctf_kernel_info_t;
 int ctf_get_kernel_info(ctf_handle_t h, ctf_kernel_info_t* out);
 

@@ -69,7 +69,7 @@ class CtfSizes(C.Structure):
 
 class CtfKernelInfo(C.Structure):
     _fields_ = [("persistent", C.c_int), ("logic_warps", C.c_int), ("stream_warps", C.c_int), ("ctas", C.c_int),
-                ("min_envs_for_persistent", C.c_int64)]
+                ("min_envs_for_persistent", C.c_int64), ("warp_per_env_ctas_per_sm", C.c_int), ("reserved", C.c_int)]
 
 
 class NativeError(RuntimeError):

@@ -1091,6 +1091,7 @@ struct ctf_env {
     int ws_logic, ws_stream, ws_ctas;   // logic / stream warps per CTA, CTAs in the grid
     long long ws_min_envs;   // batches below this use the warp-per-env kernel
     int n_sm;
+    int k_step_ctas_per_sm;  // resident-CTA cap of the warp-per-env kernels (0: whatever fits)
     size_t ws_smem_bytes;
 };
 
@@ -1266,7 +1267,7 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
     h->seed = seed; h->env_id_base = env_id_base;
     const size_t lut_bytes = (CTF_U8_LUT && obs_dtype == CTF_OBS_U8) ? 2048 : 0;   // kLutBytes<uint8_t>
     h->smem_bytes = lut_bytes + (size_t)h->plan.warp_smem_bytes * kWarpsPerCta;
-    h->faults = nullptr; h->actions_stage = nullptr; h->rewards_stage = nullptr; h->dones_stage = nullptr;
+    h->k_step_ctas_per_sm = 0;   // decided below, once the SM count is known
     DeviceGuard guard(device);
     cudaError_t e = guard.err;
     if (e == cudaSuccess) e = cudaMalloc(&h->faults, sizeof(uint32_t));
@@ -1295,13 +1296,46 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
         return fail(CTF_ERR_INVALID, "CTF_WS_LOGIC / CTF_WS_STREAM / CTF_WS_CTAS_PER_SM out of range");
     }
     h->n_sm = n_sm;
+    // Resident CTAs per SM of the warp-per-env kernels.  Registers allow 9 (36 warps); when the step is bound by the
+    // observation stream, FEWER concurrent streams write faster (8_arena float32 B = 65536: 9 -> 1.001 ms, 7 -> 0.989,
+    // 5 -> 0.980, 4 -> 0.982; 7_gridlocked 0.551 -> 0.536; bf16 0.526 -> 0.516), when it is bound by the env logic they
+    // are slower (uint8 0.283 -> 0.347, 0_the_split 0.174 -> 0.229): profiles/r02_ab_residency*.log.  So blocks of
+    // >= 6 KB per agent run with 5 CTAs per SM when there are many waves of them, and with the cap in 5..9 that fills
+    // the last wave best when there are few (B = 16384: 7).  The cap is applied by padding dynamic shared memory.
+    {
+        int cap = env_int("CTF_K_STEP_CTAS_PER_SM", -1);
+        if (cap < 0) {
+            cap = 0;
+            const size_t obs_bytes_per_agent = (size_t)h->plan.C * h->plan.GG * (obs_dtype == CTF_OBS_F32 ? 4 : (obs_dtype == CTF_OBS_U8 ? 1 : 2));
+            if (obs_bytes_per_agent >= 6000 && n_sm > 0) {
+                const double ctas_per_sm_total = (double)((num_envs + kWarpsPerCta - 1) / kWarpsPerCta) / n_sm;
+                if (ctas_per_sm_total >= 64.0) {
+                    cap = 5;
+                } else {
+                    double best = -1.0;
+                    for (int c = 5; c <= 9; ++c) {   // fill of the last wave; ties go to the smaller cap
+                        const double waves = ctas_per_sm_total / c, full = (double)(long long)(waves + 0.999999);
+                        const double fill = full > 0 ? waves / full : 0.0;
+                        if (fill > best + 1e-9) { best = fill; cap = c; }
+                    }
+                }
+            }
+        }
+        h->k_step_ctas_per_sm = cap;
+        if (cap > 0) {
+            const size_t want = (size_t)(227 * 1024) / (size_t)cap - 1024;
+            if (want > h->smem_bytes) h->smem_bytes = want;
+        }
+    }
     h->ws_ctas = n_sm * ctas_per_sm;
     h->ws_smem_bytes = lut_bytes + (size_t)kWsCtlBytes + (size_t)h->plan.warp_smem_bytes * h->ws_logic;
     // below ~4 envs per logic warp the persistent kernel is all ramp-up and tail: use the warp-per-env kernel
     h->ws_min_envs = (long long)env_int("CTF_WS_MIN_ENVS", 4 * h->ws_ctas * h->ws_logic);
     if (env_int("CTF_WS", 0) != 1 || num_envs > 0x7FFFFFFFll) h->ws_min_envs = 0x7FFFFFFFFFFFFFFFll;
-    const int smem = (int)h->smem_bytes;
-    const int ws_smem = (int)h->ws_smem_bytes;
+    // The attribute is per kernel, not per handle: give every kernel a ceiling that covers any handle's launch (another
+    // handle with a smaller footprint must not lower it under this one's), not this handle's own size.
+    const int smem = h->smem_bytes > 100 * 1024 ? (int)h->smem_bytes : 100 * 1024;
+    const int ws_smem = h->ws_smem_bytes > 200 * 1024 ? (int)h->ws_smem_bytes : 200 * 1024;
 #define CTF_SET_SMEM(K, BYTES) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)
 #define CTF_SET_SMEM_T(T)                                                                                       \
     CTF_SET_SMEM((k_step<T, false>), smem); CTF_SET_SMEM((k_step<T, true>), smem);                             \
@@ -1497,6 +1531,7 @@ extern "C" int ctf_get_kernel_info(ctf_handle_t h, ctf_kernel_info_t* out) {
     out->persistent = h->B >= h->ws_min_envs ? 1 : 0;
     out->logic_warps = h->ws_logic; out->stream_warps = h->ws_stream; out->ctas = h->ws_ctas;
     out->min_envs_for_persistent = h->ws_min_envs;
+    out->warp_per_env_ctas_per_sm = h->k_step_ctas_per_sm;
     return CTF_OK;
 }
 

@@ -17,7 +17,7 @@ from marl_ctf_development_b200 import GridworldCtfGPU, experiment_env_config  # 
 
 
 def time_shape(args, env_vars):
-    for k in ("CTF_WS", "CTF_WS_LOGIC", "CTF_WS_STREAM", "CTF_WS_CTAS_PER_SM", "CTF_WS_MIN_ENVS"):
+    for k in ("CTF_WS", "CTF_WS_LOGIC", "CTF_WS_STREAM", "CTF_WS_CTAS_PER_SM", "CTF_WS_MIN_ENVS", "CTF_K_STEP_CTAS_PER_SM"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env_vars.items()})
     dev = torch.device("cuda", 0)
@@ -71,7 +71,11 @@ def main():
     ap.add_argument("--shapes", default="quick")
     args = ap.parse_args()
     shapes = [{"CTF_WS": 0}]
-    if args.shapes == "quick":
+    if args.shapes == "residency":   # resident CTAs per SM of the warp-per-env kernel
+        shapes = [{"CTF_WS": 0, "CTF_K_STEP_CTAS_PER_SM": n} for n in (9, 8, 7, 6, 5, 4)]
+    if args.shapes == "residency":
+        grid = []
+    elif args.shapes == "quick":
         grid = [(16, 8, 1), (12, 8, 1), (20, 8, 1), (24, 8, 1), (16, 4, 1), (8, 4, 2), (12, 4, 2)]
     elif args.shapes == "default":
         grid = []
