@@ -1340,7 +1340,7 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
 #define CTF_SET_SMEM_T(T)                                                                                       \
     CTF_SET_SMEM((k_step<T, false>), smem); CTF_SET_SMEM((k_step<T, true>), smem);                             \
     CTF_SET_SMEM((k_reset<T, false>), smem); CTF_SET_SMEM((k_reset<T, true>), smem); CTF_SET_SMEM((k_observe<T>), smem); \
-    CTF_SET_SMEM((k_step_ws<T, false>), ws_smem); CTF_SET_SMEM((k_step_ws<T, true>), ws_smem)
+    CTF_SET_SMEM((k_step_ws<T, false>), ws_smem); CTF_SET_SMEM((k_step_ws<T, true>), ws_smem); CTF_SET_SMEM((k_unpack<T>), smem)
     CTF_SET_SMEM_T(float); CTF_SET_SMEM_T(uint8_t); CTF_SET_SMEM_T(__half); CTF_SET_SMEM_T(__nv_bfloat16);
 #undef CTF_SET_SMEM_T
 #undef CTF_SET_SMEM
@@ -1502,7 +1502,15 @@ extern "C" int ctf_unpack_obs(ctf_handle_t h, const uint32_t* packed, void* out,
     while (chunk > 1 && ((size_t)(chunk * nbits) / 8 + (size_t)chunk * wpa * 4) > 40 * 1024) --chunk;   // static shared-memory budget
     const int bits_words = (((chunk * nbits + 128 + 31) / 32 + 1) + 15) / 16 * 16;
     const unsigned grid = (unsigned)((n_agent_blocks + chunk - 1) / chunk);
-    const size_t smem = ((size_t)bits_words + (size_t)chunk * wpa) * sizeof(uint32_t) + ((CTF_U8_LUT && out_dtype == CTF_OBS_U8) ? 2048 : 0);
+    size_t smem = ((size_t)bits_words + (size_t)chunk * wpa) * sizeof(uint32_t) + ((CTF_U8_LUT && out_dtype == CTF_OBS_U8) ? 2048 : 0);
+    // like k_step: fewer resident CTAs = fewer concurrent write streams (profiles/r02_unpack_residency.log)
+    // float32 6 777 -> 6 838 GB/s and bf16 6 600 -> 6 703 at 5 CTAs per SM, uint8 (issue-bound) 6 365 -> 5 239: capped for >= 2-byte elements
+    static const int unpack_ctas_env = env_int("CTF_UNPACK_CTAS_PER_SM", -1);
+    const int unpack_ctas = unpack_ctas_env >= 0 ? unpack_ctas_env : (elem >= 2 ? 5 : 0);
+    if (unpack_ctas > 0) {
+        const size_t want = (size_t)(227 * 1024) / (size_t)unpack_ctas - 1024;
+        if (want > smem) smem = want;
+    }
     with_obs_type(out_dtype, [&](auto tag) {
         using T = decltype(tag);
         k_unpack<T><<<grid, kUnpackThreads, smem, s>>>(packed, static_cast<T*>(out), n_agent_blocks, nbits, wpa, chunk, bits_words);
