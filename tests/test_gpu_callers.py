@@ -167,3 +167,49 @@ def test_unmodified_get_single_rollout_runs_on_the_cuda_backend():
     assert np.array_equal(out[8].numpy(), want["next_grid_state"][k])
     assert np.array_equal(bits(out[9].numpy()), bits(want["next_metadata_state"][k]))
     assert np.array_equal(out[10].numpy(), want["next_done"][k])
+
+
+@needs_reference
+def test_unmodified_utils_duel_json_runs_on_the_cuda_backend(tmp_path):
+    """utils.duel_json (utils.py:728-814), unmodified, on the single-env view: the file it writes is byte-identical to the
+    one it wrote on the reference env (it reads env.grid, agent_positions, has_flag and metrics every step)."""
+    from marl_ctf_development_b200 import GridworldCtf
+
+    duel_json = rs.caller_modules()["utils"].duel_json
+    name, exp, overrides, max_steps, env_id = cc.CASES["duel_jsons"][0]
+    want = cc.load_duel_json(name)
+    agent, opponent = cc.policies(exp, overrides, (5, 6))
+    env = GridworldCtf(**cc.env_config(exp, overrides), seed=cc.SEED, env_id=env_id)
+    path = tmp_path / "trace.json"
+    duel_json(env, agent, opponent, max_steps=max_steps, fname=str(path))
+    assert path.read_bytes() == want
+
+
+@needs_reference
+@pytest.mark.parametrize("exp", ["8_arena", "0_the_split"])
+def test_unmodified_league_trainer_builds_its_objects_on_the_cuda_backend(exp, monkeypatch):
+    """LeagueTrainer._init_objects (league_training.py:59-146) with the one-line import change of INTEGRATION.md §1: the env,
+    its dims, the symmetry verdict, the per-team agent types and the Agent networks come out as with the reference env."""
+    import marl_ctf_development_b200 as ours
+
+    lt = rs.caller_modules()["league_training"]
+    import runpy, os
+
+    cfg_cls = runpy.run_path(os.path.join(rs.REF_ROOT, exp + rs.REF_SUFFIX), run_name="ctf_test")["TrainingConfig"]
+    args = cfg_cls()
+    with rs._in_ref_dir():
+        ref_trainer = lt.LeagueTrainer(args)                       # the reference env (gridworld_ctf.GridworldCtf)
+    monkeypatch.setattr(lt, "GridworldCtf", ours.GridworldCtf)      # "from marl_ctf_development_b200 import GridworldCtf"
+    gpu_trainer = lt.LeagueTrainer(cfg_cls())
+    assert isinstance(gpu_trainer.env, ours.GridworldCtf)
+    for attr in ("local_grid_dims", "local_metadata_dims", "n_channels", "symmetric_teams"):
+        assert getattr(gpu_trainer, attr) == getattr(ref_trainer, attr), attr
+    assert dict(gpu_trainer.agent_team_types) == dict(ref_trainer.agent_team_types)
+    assert gpu_trainer.metlog.agent_indiv_idxs == ref_trainer.metlog.agent_indiv_idxs
+    a, b = gpu_trainer.main_agents_t1[0], ref_trainer.main_agents_t1[0]
+    assert [tuple(p.shape) for p in a.parameters()] == [tuple(p.shape) for p in b.parameters()]
+    # and the first thing train_league does with it: one unmodified duel between two of its agents
+    torch.manual_seed(0)
+    i, j, result = rs.caller_modules()["utils"].duel(gpu_trainer.env, a, gpu_trainer.main_agents_t1[-1], (0, 1), return_result=True,
+                                                      device="cpu", max_steps=12)
+    assert (i, j) == (0, 1) and result in (-1, 0, 1) and gpu_trainer.env.env_step_count == 13
