@@ -69,11 +69,14 @@ def main():
     ap.add_argument("--packed", action="store_true")
     ap.add_argument("--no-dense", action="store_true")
     ap.add_argument("--shapes", default="quick")
+    ap.add_argument("--k-step-ctas", type=int, default=-1, help="resident-CTA cap of the warp-per-env kernel for every shape (-1: heuristic)")
     args = ap.parse_args()
     shapes = [{"CTF_WS": 0}]
+    if args.shapes == "kstep":       # the warp-per-env kernel only
+        shapes = [{"CTF_WS": 0}]
     if args.shapes == "residency":   # resident CTAs per SM of the warp-per-env kernel
         shapes = [{"CTF_WS": 0, "CTF_K_STEP_CTAS_PER_SM": n} for n in (9, 8, 7, 6, 5, 4)]
-    if args.shapes == "residency":
+    if args.shapes in ("residency", "kstep"):
         grid = []
     elif args.shapes == "quick":
         grid = [(16, 8, 1), (12, 8, 1), (20, 8, 1), (24, 8, 1), (16, 4, 1), (8, 4, 2), (12, 4, 2)]
@@ -87,6 +90,8 @@ def main():
     for l, s, c in grid:
         shapes.append({"CTF_WS": 1, "CTF_WS_LOGIC": l, "CTF_WS_STREAM": s, "CTF_WS_CTAS_PER_SM": c, "CTF_WS_MIN_ENVS": 1})
     for sh in shapes:
+        if args.k_step_ctas >= 0:
+            sh = dict(sh, CTF_K_STEP_CTAS_PER_SM=args.k_step_ctas)
         try:
             print(json.dumps(dict(time_shape(args, sh), experiment=args.experiment, envs=args.envs, obs_dtype=args.obs_dtype)), flush=True)
         except Exception as exc:  # a shape that does not fit (shared memory) is reported, not fatal
