@@ -75,8 +75,9 @@ def load_env_config(obj: dict) -> dict:
 _cache = None
 
 
-def experiment_names() -> list[str]:
-    return list(_load().keys())
+def experiment_names(alternative: bool = False) -> list[str]:
+    """The nine experiment scripts of the reference; with alternative=True the alt_exp/*.py variants ('alt_exp/<name>')."""
+    return [k for k in _load().keys() if k.startswith("alt_exp/") == bool(alternative)]
 
 
 def _load() -> dict:

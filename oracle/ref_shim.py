@@ -212,6 +212,19 @@ def experiment_env_config(name: str) -> dict:
     return ns["TrainingConfig"]().env_config
 
 
+def alt_experiment_names() -> list:
+    """Names of the alternative experiment scripts (alt_exp/*.py, "not used in final report"); source tree only."""
+    d = os.path.join(SRC_ROOT, "alt_exp")
+    return sorted(f[:-3] for f in os.listdir(d) if f.endswith(".py")) if source_tree_available() and os.path.isdir(d) else []
+
+
+def alt_experiment_env_config(name: str) -> dict:
+    reference_modules()
+    with _in_ref_dir():
+        ns = runpy.run_path(os.path.join(SRC_ROOT, "alt_exp", name + ".py"), run_name="ctf_ref_shim")
+    return ns["TrainingConfig"]().env_config
+
+
 def make_reference_env(env_config: dict):
     """Unmodified reference env, global RNGs untouched (caller seeds them)."""
     gw, _ = reference_modules()

@@ -3,7 +3,7 @@
     python tests/golden/make_golden.py
 
 Writes
-  marl_ctf_development_b200/data/experiments.json   env_config of the nine experiment scripts (inputs)
+  marl_ctf_development_b200/data/experiments.json   env_config of the nine experiment scripts and of alt_exp/*.py (inputs)
   tests/golden/trace_<experiment>_<policy>.npz      per-step outputs of the reference GridworldCtf with the
                                                     Philox site draws injected (oracle/ref_shim.py)
   tests/golden/json_reset_states.json               reset-state content of the reference's json/*.json traces
@@ -124,6 +124,8 @@ def json_reset_states() -> dict:
 def main():
     assert rs.available(), "needs /root/reference"
     exps = {name: dump_env_config(rs.experiment_env_config(name)) for name in rs.EXPERIMENTS}
+    # the alternative experiment scripts (alt_exp/*.py: arena, arena_ii, jailbreak_ii, ... maps) as inputs only
+    exps.update({"alt_exp/" + name: dump_env_config(rs.alt_experiment_env_config(name)) for name in rs.alt_experiment_names()})
     data_dir = os.path.join(ROOT, "marl_ctf_development_b200", "data")
     os.makedirs(data_dir, exist_ok=True)
     with open(os.path.join(data_dir, "experiments.json"), "w") as f:

@@ -24,6 +24,8 @@ EXPECTED = {
 
 def test_nine_experiments_present():
     assert len(experiment_names()) == 9
+    alt = experiment_names(alternative=True)        # alt_exp/*.py: arena, arena_ii, jailbreak_ii, ... maps
+    assert len(alt) == 8 and all(compiled(name).N_AGENTS >= 2 for name in alt)
 
 
 @pytest.mark.parametrize("exp", sorted(EXPECTED))

@@ -156,6 +156,14 @@ def test_other_experiments_against_oracle(exp):
     _run_against_oracle(exp, 128, 260, "builder", seed=19, obs_every=20, stats="full")
 
 
+@pytest.mark.parametrize("exp", ["alt_exp/1_fence_ii", "alt_exp/2_jailbreak_ii", "alt_exp/3_one_way_out_ii", "alt_exp/4_keyhole_ii",
+                                 "alt_exp/5_skittles_ii", "alt_exp/6_the_wall_ii", "alt_exp/8_arena", "alt_exp/8_arena_ii"])
+def test_alternative_experiments_against_oracle(exp):
+    """The reference's alt_exp/*.py configs (other maps of scenarios.py); the oracle is pinned to the reference on them in
+    test_oracle_vs_reference.py::test_alternative_experiment_configs_also_match."""
+    _run_against_oracle(exp, 96, 150, "builder", seed=23, obs_every=25, stats="full")
+
+
 @pytest.mark.parametrize("name,exp,overrides,kind", KWARG_CASES, ids=CASE_IDS)
 def test_constructor_keyword_variations(name, exp, overrides, kind):
     """The ctor keywords / team layouts pinned against the reference in test_oracle_vs_reference.py, on the GPU."""

@@ -278,3 +278,31 @@ def test_full_episode_with_the_aggressive_policy(exp):
     st = orc.state()
     assert np.array_equal(rs.agent_metrics(ref), st["stats"])
     assert np.array_equal(np.stack([ref.metrics["agent_visitation_maps"][i] for i in range(ce.N_AGENTS)]), st["visits"])
+
+
+@pytest.mark.parametrize("name", rs.alt_experiment_names() or ["<no alt_exp in this tree>"])
+def test_alternative_experiment_configs_also_match(name):
+    """alt_exp/*.py (arena, arena_ii, jailbreak_ii, ... maps that the nine main scripts do not use): every scenario dict
+    of scenarios.py that has a script goes through the config compiler and the oracle, step by step against the reference."""
+    if name.startswith("<"):
+        pytest.skip("alt_exp scripts need the reference source tree")
+    ec = rs.alt_experiment_env_config(name)
+    ce = compile_config(**ec)
+    ref = rs.make_injected_env(ec, seed=7, env_id=77)
+    orc = OracleEnv(ce, seed=7, env_id=77)
+    assert env_dims(ce) == ref.get_env_dims()
+    assert [int(t) for t in ce.TILES_USED] == [int(t) for t in ref.TILES_USED]
+    pol = traces.make_policy("builder" if 3 in ce.AGENT_TYPES.values() else "seek", ce)
+    rng = np.random.default_rng(11)
+    for t in range(150):
+        s0 = rs.snapshot(ref, ce.cfg.hp_scale)
+        a = pol(rng, s0["pos"], s0["has_flag"])
+        _, rr, rd = ref.step(a.tolist())
+        orr, od = orc.step(a)
+        assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"{name} t={t}")
+        assert rd == od and np.array_equal(bits(np.array(rr, dtype=np.float32)), bits(orr))
+        if t % 10 == 0:
+            ro, rm = rs.observations(ref)
+            oo, om = orc.observe()
+            assert np.array_equal(ro, oo) and np.array_equal(bits(rm), bits(om))
+    assert np.array_equal(rs.agent_metrics(ref), orc.state()["stats"])
