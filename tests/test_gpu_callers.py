@@ -213,3 +213,48 @@ def test_unmodified_league_trainer_builds_its_objects_on_the_cuda_backend(exp, m
     i, j, result = rs.caller_modules()["utils"].duel(gpu_trainer.env, a, gpu_trainer.main_agents_t1[-1], (0, 1), return_result=True,
                                                       device="cpu", max_steps=12)
     assert (i, j) == (0, 1) and result in (-1, 0, 1) and gpu_trainer.env.env_step_count == 13
+
+
+@needs_reference
+def test_reference_ppo_update_runs_on_batched_gpu_rollouts():
+    """collect_rollout replaces the num_envs Ray rollouts of train_ppo (ppo.py:326-396); everything after —
+    the reference's own calculate_advantages (:133-172) and optimise (:174-242), unmodified, with reference Agent networks —
+    runs on its arrays because they have the same [num_steps * apt, num_envs, ...] layout."""
+    import types
+
+    import torch.optim as optim
+
+    from marl_ctf_development_b200 import GridworldCtfGPU
+    from marl_ctf_development_b200.rollout import collect_rollout
+
+    mods = rs.caller_modules()
+    Agent, PPOTrainer = mods["agent_network"].Agent, mods["ppo"].PPOTrainer
+    ec = cc.env_config("8_arena", {"GAME_STEPS": 32})
+    B, T = 16, 32
+    env = GridworldCtfGPU(**ec, num_envs=B, device="cuda:0", seed=5, reverse_team1_actions=True)
+    dims = env.get_env_dims()
+    torch.manual_seed(1)
+    agent = Agent(9, env.n_channels, env.GRID_SIZE, env.meta_size, "cuda").cuda()
+    opponent = Agent(9, env.n_channels, env.GRID_SIZE, env.meta_size, "cuda").cuda()
+    args = types.SimpleNamespace(device="cuda", num_steps=T, num_envs=B, num_minibatches=4, update_epochs=2, gae=True, gamma=0.99,
+                                 gae_lambda=0.95, norm_adv=True, clip_coef=0.2, clip_vloss=True, ent_coef=0.01, vf_coef=0.5,
+                                 max_grad_norm=0.5, target_kl=None, learning_rate=2.5e-4)
+    tr = PPOTrainer(args, dims[0], dims[2])
+    apt = env.N_AGENTS // 2                                      # what train_ppo sets up (ppo.py:274-296)
+    tr.device, tr.num_agents_per_team, tr.num_steps = "cuda", apt, T * apt
+    tr.batch_size = B * T * apt
+    tr.minibatch_size = tr.batch_size // args.num_minibatches
+    tr.optimizer = optim.Adam(agent.parameters(), lr=args.learning_rate, eps=1e-5)
+    before = [p.detach().clone() for p in agent.parameters()]
+    for update in range(2):
+        ro = collect_rollout(env, agent, opponent, train_team1=True)          # one 32-step episode of all 16 envs
+        (grid_states, metadata_states, actions, use_action_mask, logprobs, rewards, dones, values,
+         next_grid_state, next_metadata_state, next_done) = ro.as_reference_arrays()
+        assert tuple(grid_states.shape) == (T * apt, B) + dims[0] and float(next_done) == 1.0
+        advantages, returns = tr.calculate_advantages(agent, next_grid_state, next_metadata_state, rewards, next_done, dones, values)
+        assert tuple(advantages.shape) == (T * apt, B) and bool(torch.isfinite(advantages).all())
+        v_loss, pg_loss, ent = tr.optimise(agent, grid_states.reshape((-1,) + dims[0]), metadata_states.reshape((-1,) + dims[2]),
+                                           logprobs.reshape(-1), actions.reshape(-1), use_action_mask.reshape(-1),
+                                           advantages.reshape(-1), returns.reshape(-1), values.reshape(-1))
+        assert all(np.isfinite(x) for x in (v_loss, pg_loss, ent)) and ent > 0
+    assert any(not torch.equal(a, b) for a, b in zip(before, agent.parameters()))
