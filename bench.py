@@ -513,6 +513,15 @@ def run_ours(args) -> dict | None:
             side_config(args, "0_the_split", 4096, dev, torch, peak, steps=50, graph=True),     # BASELINE.json configs[1]
             side_config(args, "7_gridlocked", 16384, dev, torch, peak, steps=50),               # BASELINE.json configs[2]
         ]
+    if not args.no_side and EXPERIMENT == "8_arena":
+        # BASELINE.json configs[4]: self-play rollout with the agent_network-style policy fed from the env's buffers, at the
+        # headline B on every rank (stock cuDNN policy inference is ~98 % of this loop; it is outside the hot path)
+        import bench_rollout
+
+        ra = bench_rollout.parse_args(["--envs", str(B), "--steps", "3", "--warmup", "1", "--graph", "--channels-last"])
+        ro = bench_rollout.measure(ra)
+        if rank == 0:
+            result["config5_rollout"] = ro
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline_sample(N)
     if world > 1:

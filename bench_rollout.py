@@ -23,13 +23,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def main():
-    import torch
-    import torch.distributed as dist
-
-    from marl_ctf_development_b200 import GridworldCtfGPU, experiment_env_config
-    from marl_ctf_development_b200.policy import CtfPolicy
-
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU (BASELINE.json config 5: 65536)")
     ap.add_argument("--graph", action="store_true", help="capture policy forwards + step + rollout store in one CUDA graph")
@@ -41,12 +35,20 @@ def main():
     ap.add_argument("--channels-last", action="store_true", help="run the convolutions in NHWC (stock torch option)")
     ap.add_argument("--obs-dtype", choices=["float32", "bfloat16"], default=None,
                     help="env observation buffer type (default: bfloat16 when the policy runs in bf16)")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def measure(args):
+    """Runs the loop on this rank's GPU (torch.distributed already initialised when WORLD_SIZE > 1).
+    Returns the result dict on rank 0, None elsewhere.  bench.py calls this for its config-5 side figure."""
+    import torch
+    import torch.distributed as dist
+
+    from marl_ctf_development_b200 import GridworldCtfGPU, experiment_env_config
+    from marl_ctf_development_b200.policy import CtfPolicy
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = args.envs
@@ -136,9 +138,10 @@ def main():
     ms_full = timed(args.steps, True)
     ms_env = timed(args.steps, False)
     ms_pol = timed(args.steps, True, False)
+    result = None
     if rank == 0:
         total = world * B * N * args.steps
-        print(json.dumps({
+        result = ({
             "metric": "rollout_agent_steps_per_sec", "value": total / (ms_full * 1e-3), "unit": "agent-steps/s",
             "env_only_value": total / (ms_env * 1e-3), "policy_only_value": total / (ms_pol * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -151,7 +154,24 @@ def main():
                                    f"{', channels_last' if args.channels_last else ''}; env-only = step + packed rollout store",
                        "envs_per_gpu": B},
             "data": "synthetic (random-init policies)",
-        }), flush=True)
+        })
+    env.close()
+    del env, ring, ring_meta, pols, graphs
+    torch.cuda.empty_cache()
+    return result
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    args = parse_args()
+    world, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    result = measure(args)
+    if result is not None:
+        print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -312,6 +312,10 @@ def test_bench_contract_keys():
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 2048 * 8
     assert "workload" in d["config"] and "model" not in d["config"]
+    # BASELINE configs[1], [2] and [4] ride along in the same line (side_configs, config5_rollout)
+    assert len(d["side_configs"]) == 2 and all(s["ms_per_step"] > 0 for s in d["side_configs"])
+    assert d["config5_rollout"]["value"] > 0 and d["config5_rollout"]["env_only_value"] > d["config5_rollout"]["value"]
+    assert d["episode_stats_checksum"] != 0 and d["clocks"]["samples"] >= 2
 
 
 def test_integration_md_ctypes_stub_runs_as_written():
