@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CTF_ABI_VERSION 3
+#define CTF_ABI_VERSION 4
 
 #define CTF_MAX_AGENTS 8    /* largest AGENT_STARTING_POSITIONS in scenarios.py has 8 entries */
 #define CTF_MAX_GRID 16     /* GRID_SIZE <= 16 (shipped maps: 11, 13, 15) */
@@ -129,6 +129,17 @@ typedef struct ctf_config {
     uint8_t type_action_mask[CTF_N_TYPES];               /* AGENT_TYPE_ACTION_MASK (:218-223) */
     uint8_t chan_lut[2][16];               /* [observer team][tile code] -> channel 1..C-1, 0 = no channel (O1) */
     uint8_t grid_template[CTF_MAX_CELLS];  /* load_scenario() result, row-major G x G */
+
+    /* HP representation.  0: exact fixed point (the *_q fields, hp_scale) — every shipped configuration.  1: IEEE doubles
+       (the *_f fields below), for HP / damage / heal / vault quantities that are not dyadic rationals (e.g. heal 0.1):
+       the device then performs the reference's Python float operations one by one (gridworld_ctf.py:648-657, 818-824,
+       785, 845-846, 1040) and keeps HP in state.hp. */
+    int32_t hp_float;
+    int32_t reserved0;
+    double hp_max_f[CTF_N_TYPES];          /* AGENT_TYPE_HP */
+    double damage_f[CTF_N_TYPES];          /* AGENT_TYPE_DAMAGE */
+    double damage_boosted_f[CTF_N_TYPES];  /* AGENT_TYPE_DAMAGE * GUARDIAN_DAMAGE_MULTIPLIER (one float multiplication) */
+    double heal_f, vault_cost_f, vault_min_f;
 } ctf_config_t;
 
 /* Device buffers of the B resident environments (SoA of field groups, env-major). */
@@ -138,6 +149,7 @@ typedef struct ctf_state {
     uint32_t* envs;   /* [B][4]: env_step_count, episode, team_flag_captures[0], team_flag_captures[1] */
     uint32_t* stats;  /* [B][13][N] counters, or NULL when created with stats_level 0 */
     uint8_t* visits;  /* [B][N][G*G] uint8 visitation maps (wrap at 256), or NULL unless stats_level 2 */
+    double* hp;       /* [B][N] agent HP as doubles when cfg.hp_float is set (the hp_q field of `agents` is then unused), else NULL */
 } ctf_state_t;
 
 /* Device output buffers of one reset()/step(). Any pointer may be NULL to skip that output. */
@@ -158,6 +170,7 @@ typedef struct ctf_sizes {
     size_t obs_elems_per_env, meta_elems_per_env;
     size_t obs_bits_bytes;       /* bytes of outputs.obs_bits */
     size_t bits_words_per_agent; /* ceil(C*G*G / 32) */
+    size_t hp_bytes;             /* bytes of state.hp (0 unless cfg.hp_float) */
 } ctf_sizes_t;
 
 typedef struct ctf_env* ctf_handle_t;

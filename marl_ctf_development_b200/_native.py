@@ -27,7 +27,7 @@ EXPORTS = (
     "ctf_step_host",
     "ctf_get_kernel_info",
 )
-ABI_VERSION = 3
+ABI_VERSION = 4
 FAULT_BAD_ACTION, FAULT_RESPAWN_BLOCKED = 1, 2
 
 
@@ -38,6 +38,7 @@ class CtfState(C.Structure):
         ("envs", C.c_void_p),
         ("stats", C.c_void_p),
         ("visits", C.c_void_p),
+        ("hp", C.c_void_p),
     ]
 
 
@@ -63,6 +64,7 @@ class CtfSizes(C.Structure):
             "meta_elems_per_env",
             "obs_bits_bytes",
             "bits_words_per_agent",
+            "hp_bytes",
         )
     ]
 

@@ -89,6 +89,14 @@ class CtfConfig(C.Structure):
         ("type_action_mask", C.c_uint8 * N_TYPES),
         ("chan_lut", (C.c_uint8 * 16) * 2),
         ("grid_template", C.c_uint8 * MAX_CELLS),
+        ("hp_float", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("hp_max_f", C.c_double * N_TYPES),
+        ("damage_f", C.c_double * N_TYPES),
+        ("damage_boosted_f", C.c_double * N_TYPES),
+        ("heal_f", C.c_double),
+        ("vault_cost_f", C.c_double),
+        ("vault_min_f", C.c_double),
     ]
 
 
@@ -265,18 +273,35 @@ def compile_config(
         + [boosted[t] for t in range(N_TYPES)]
         + [AGENT_HP_HEALING_PER_STEP, VAULT_HP_COST, VAULT_MIN_HP]
     )
-    s = _hp_scale(quantities)
-    q = lambda v: int(Fraction(v) * s)  # noqa: E731
-    if max(q(v) for v in quantities) > 32000 or min(q(AGENT_TYPE_HP[t]) for t in range(N_TYPES)) <= 0:
-        raise ValueError("HP quantities out of the int16 fixed-point range")
+    try:
+        s = _hp_scale(quantities)
+        if max(int(Fraction(v) * s) for v in quantities) > 32000:
+            raise ValueError("HP quantities out of the int16 fixed-point range")
+    except ValueError:
+        s = 0
+    if min(AGENT_TYPE_HP[t] for t in range(N_TYPES)) <= 0:
+        raise ValueError("AGENT_TYPE_HP must be positive")
     cfg.hp_scale = s
-    cfg.heal_q = q(AGENT_HP_HEALING_PER_STEP)
-    cfg.vault_cost_q = q(VAULT_HP_COST)
-    cfg.vault_min_q = q(VAULT_MIN_HP)
+    # the float fields are always filled: what the reference computes with (Python floats; int * float is exact for these)
+    cfg.heal_f, cfg.vault_cost_f, cfg.vault_min_f = float(AGENT_HP_HEALING_PER_STEP), float(VAULT_HP_COST), float(VAULT_MIN_HP)
     for t in range(N_TYPES):
-        cfg.hp_max_q[t] = q(AGENT_TYPE_HP[t])
-        cfg.damage_q[t] = q(AGENT_TYPE_DAMAGE[t])
-        cfg.damage_boosted_q[t] = q(boosted[t])
+        cfg.hp_max_f[t] = float(AGENT_TYPE_HP[t])
+        cfg.damage_f[t] = float(AGENT_TYPE_DAMAGE[t])
+        cfg.damage_boosted_f[t] = float(AGENT_TYPE_DAMAGE[t] * GUARDIAN_DAMAGE_MULTIPLIER)   # :818, one multiplication
+    if s:
+        # every quantity is a dyadic rational: exact fixed point on the device (all shipped configurations)
+        q = lambda v: int(Fraction(v) * s)  # noqa: E731
+        cfg.hp_float = 0
+        cfg.heal_q = q(AGENT_HP_HEALING_PER_STEP)
+        cfg.vault_cost_q = q(VAULT_HP_COST)
+        cfg.vault_min_q = q(VAULT_MIN_HP)
+        for t in range(N_TYPES):
+            cfg.hp_max_q[t] = q(AGENT_TYPE_HP[t])
+            cfg.damage_q[t] = q(AGENT_TYPE_DAMAGE[t])
+            cfg.damage_boosted_q[t] = q(boosted[t])
+    else:
+        # e.g. AGENT_HP_HEALING_PER_STEP=0.1: HP as IEEE doubles, the reference's float operations one by one
+        cfg.hp_float = 1
 
     # u = w / 2**32 < p  <=>  w < ceil(p * 2**32)
     thr = Fraction(TAG_PROBABILITY) * (1 << 32)

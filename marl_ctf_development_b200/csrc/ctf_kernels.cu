@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <new>
+#include <type_traits>
 
 #include "../../include/ctf_b200.h"
 
@@ -67,6 +68,9 @@ struct DevPlan {
     int heal_q, vault_cost_q, vault_min_q;
     int zone_distance, guardian_distance, tagging_range, max_agent_blocks, block_pickup_value;
     int hp_max_q[4], damage_q[4], damage_boosted_q[4];
+    // hp_float: HP as IEEE doubles, every operation rounded like the reference's Python floats (non-dyadic configs)
+    int hp_float;
+    double hp_max_f[4], damage_f[4], damage_boosted_f[4], heal_f, vault_cost_f, vault_min_f;
     int warp_smem_bytes, list_off, bits_off;
     unsigned char team[8], type[8], tile[8], start_r[8], start_c[8], obs_rev[8], meta_hp_src[8];
     signed char my_slot[8];        // index of agent i in OPPONENTS[1 - team(i)], -1 if truncated away
@@ -86,6 +90,7 @@ struct Launch {
     uint4* envs;
     uint32_t* stats;
     uint8_t* visits;
+    double* hp;             // [B][N] when plan.hp_float
     // outputs
     void* obs;
     uint32_t* obs_bits;
@@ -450,14 +455,21 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const Launch& L, con
 // element is one shuffle.
 enum : unsigned { kMetaHp = 0, kMetaFlag = 8, kMetaPct = 16, kMetaRatio0 = 17, kMetaRatio1 = 18, kMetaOne = 19, kMetaZero = 20 };
 
-__device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int step, int caps0, int caps1,
+template <bool HPF>
+__device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, double hpd, int step, int caps0, int caps1,
                                            float* __restrict__ meta_env, int lane) {
     const int N = P.N, M = P.M;
     const int li = lane & 7;
     // hp8[i] = uint8(agent_hp[TYPE_i as agent id] / AGENT_TYPE_HP[TYPE_i])  (:1039-1041)
     const uint32_t src = __shfl_sync(kFull, me, P.meta_hp_src[li]);
     const uint32_t mine = __shfl_sync(kFull, me, li);
-    const float hp8 = (float)((ag_hp(src) / P.hp_max_q[P.type[li]]) & 0xFF);
+    float hp8;
+    if (HPF) {   // the same quotient in double, truncated like numpy's float -> uint8 store
+        const double srcd = __shfl_sync(kFull, hpd, P.meta_hp_src[li]);
+        hp8 = (float)((int)__ddiv_rn(srcd, P.hp_max_f[P.type[li]]) & 0xFF);
+    } else {
+        hp8 = (float)((ag_hp(src) / P.hp_max_q[P.type[li]]) & 0xFF);
+    }
     // the three fp64 quotients that go through float16 (:1035-1036, :1044), one per lane 16..18, in a single pass
     const int num = lane == 16 ? step : (lane == 17 ? caps0 + 1 : caps1 + 1);
     const int den = lane == 16 ? P.game_steps : (lane == 17 ? caps1 + 1 : caps0 + 1);
@@ -492,7 +504,8 @@ __device__ __forceinline__ void write_meta(const DevPlan& P, uint32_t me, int st
 // State staging
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_state(const DevPlan& P, const Launch& L, const WarpMem& w, long long env,
-                                            uint32_t me, int inv, uint4 ev, int lane) {
+                                            uint32_t me, double hpd, int inv, uint4 ev, int lane) {
+    if (P.hp_float && lane < P.N) L.hp[env * P.N + lane] = hpd;
     if (lane < kGridBytes / 16)
         st_state(reinterpret_cast<uint4*>(L.grid + env * kGridBytes) + lane, reinterpret_cast<const uint4*>(w.grid)[lane]);
     if (lane < P.N) {
@@ -537,10 +550,11 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ DevP
         reinterpret_cast<uint4*>(w.grid)[lane] = reinterpret_cast<const uint4*>(P.grid_template)[lane];
     const int li = lane & 7;
     const uint32_t me = pack_agent(P.start_r[li], P.start_c[li], 0, P.hp_max_q[P.type[li]]);
+    const double hpd = P.hp_float ? P.hp_max_f[P.type[li]] : 0.0;
     uint4 ev = make_uint4(0, 0, 0, 0);
     if (!L.first_reset) ev.y = L.envs[env].y + 1;  // episode
     __syncwarp();
-    store_state(P, L, w, env, me, 0, ev, lane);
+    store_state(P, L, w, env, me, hpd, 0, ev, lane);
     if (STATS) {
         const int ns = CTF_N_METRICS * P.N;
         for (int i = lane; i < ns; i += 32) L.stats[env * ns + i] = 0;
@@ -555,7 +569,10 @@ __global__ void __launch_bounds__(kThreads) k_reset(const __grid_constant__ DevP
     if (L.dones && lane == 0) L.dones[env] = 0;
     const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
                                                         : __ballot_sync(kFull, lane < P.N && P.obs_rev[li]);
-    if (L.meta) write_meta(P, me, 0, 0, 0, L.meta + env * (long long)P.N * P.M, lane);
+    if (L.meta) {   // not a hot kernel: the HP representation is a run-time branch here
+        if (P.hp_float) write_meta<true>(P, me, hpd, 0, 0, 0, L.meta + env * (long long)P.N * P.M, lane);
+        else write_meta<false>(P, me, 0.0, 0, 0, 0, L.meta + env * (long long)P.N * P.M, lane);
+    }
     write_obs<T>(P, L, w, env, me, rev_mask, lane, lut);
 }
 
@@ -574,15 +591,20 @@ __global__ void __launch_bounds__(kThreads) k_observe(const __grid_constant__ De
         reinterpret_cast<uint4*>(w.grid)[lane] = ld_state(reinterpret_cast<const uint4*>(L.grid + env * kGridBytes) + lane);
     const int li = lane & 7;
     uint32_t me = 0;
+    double hpd = 0.0;
     if (lane < P.N) {
         const unsigned long long rec = ld_state(L.agents + env * P.N + lane);
         me = pack_agent((int)(rec & 0xFF), (int)((rec >> 8) & 0xFF), (int)((rec >> 16) & 1), (int)(short)(rec >> 32));
+        if (P.hp_float) hpd = L.hp[env * P.N + lane];
     }
     const uint4 ev = ld_state(L.envs + env);
     __syncwarp();
     const uint32_t rev_mask = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu)
                                                         : __ballot_sync(kFull, lane < P.N && P.obs_rev[li]);
-    if (L.meta) write_meta(P, me, (int)ev.x, (int)ev.z, (int)ev.w, L.meta + env * (long long)P.N * P.M, lane);
+    if (L.meta) {
+        if (P.hp_float) write_meta<true>(P, me, hpd, (int)ev.x, (int)ev.z, (int)ev.w, L.meta + env * (long long)P.N * P.M, lane);
+        else write_meta<false>(P, me, 0.0, (int)ev.x, (int)ev.z, (int)ev.w, L.meta + env * (long long)P.N * P.M, lane);
+    }
     write_obs<T>(P, L, w, env, me, rev_mask, lane, lut);
 }
 
@@ -592,7 +614,10 @@ __global__ void __launch_bounds__(kThreads) k_observe(const __grid_constant__ De
 // One env step by one warp: state in, act / tag / respawn / heal / rewards / statistics / metadata, state out.
 // Returns the lane's agent register (position for the observation's self plane) and the per-agent reverse_grid mask;
 // the tile map of the new state is left in w.grid for the observation writer.
-template <bool STATS>
+// HPF: HP is an IEEE double per agent (plan.hp_float) instead of the fixed-point field of the agent register; every
+// operation on it is the reference's Python float operation (:648-650 vault gate, :656 vault cost, :818 damage, :824
+// lethal test, :785 respawn, :845-846 heal), so non-dyadic HP configurations stay bit-exact.
+template <bool STATS, bool HPF>
 __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, const WarpMem& w, long long env, int lane,
                                              uint32_t& rev_mask_out) {
     const int N = P.N;
@@ -619,6 +644,8 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
     }
     uint4 ev = ld_state(L.envs + env);
 #endif
+    double hpd = 0.0;   // this lane's agent's HP (HPF only; dead code otherwise)
+    if (HPF && lane < N) hpd = L.hp[env * N + lane];
     Deltas dl;
     const int my_team = P.team[li], my_type = P.type[li], my_slot = P.my_slot[li];
     const bool bad_action = lane < N && action >= CTF_N_ACTIONS;
@@ -657,6 +684,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
         const int type = P.type[a], team = P.team[a], tile = P.tile[a];
         int ar = ag_r(am), ac = ag_c(am), aflag = ag_flag(am), ahp = ag_hp(am);
         int ainv = (type == 3) ? __shfl_sync(kFull, inv, a) : 0;
+        double ahpd = HPF ? __shfl_sync(kFull, hpd, a) : 0.0;
         bool cap_now = false;
         Deltas turn;                                           // this turn's counter increments (warp-uniform)
 
@@ -664,7 +692,8 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
         const int nr = ar + P.delta[type][act_code][0], nc = ac + P.delta[type][act_code][1];
         if (nr >= 0 && nr < P.G && nc >= 0 && nc < P.G) {     // is_valid_move (:636-641)
             const int target = w.grid[nr * kRow + nc];
-            if (target == 0 && (act_code <= 3 || (act_code >= 5 && type == 2 && (ahp - P.vault_cost_q) > P.vault_min_q))) {
+            const bool can_vault = HPF ? (__dsub_rn(ahpd, P.vault_cost_f) > P.vault_min_f) : ((ahp - P.vault_cost_q) > P.vault_min_q);
+            if (target == 0 && (act_code <= 3 || (act_code >= 5 && type == 2 && can_vault))) {
                 // movement_handler (:569-612); every lane stores the same bytes
                 __syncwarp();
                 w.grid[ar * kRow + ac] = 0;
@@ -691,7 +720,10 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
                     cap_now = true;
                     bump<STATS>(turn, CTF_M_FLAG_CAPTURES, 1);
                 }
-                if (act_code >= 5 && type == 2) ahp -= P.vault_cost_q;                               // (:652-657)
+                if (act_code >= 5 && type == 2) {                                                   // (:652-657)
+                    if (HPF) ahpd = __dsub_rn(ahpd, P.vault_cost_f);
+                    else ahp -= P.vault_cost_q;
+                }
             } else if (act_code >= 5 && type == 3 && ainv > 0 && target == 0 &&
                        cheb(nr, nc, P.spawn_pos[team][0], P.spawn_pos[team][1]) > 1 &&
                        cheb(nr, nc, P.spawn_pos[1 - team][0], P.spawn_pos[1 - team][1]) > 1) {
@@ -718,6 +750,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
         }
         if (lane == a) {
             me = pack_agent(ar, ac, aflag, ahp);
+            if (HPF) hpd = ahpd;
             inv = ainv;
             captured = cap_now;
         }
@@ -728,9 +761,10 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
         bool moved_by_respawn = false;
 
         // ---------------- tagging_logic (:796-837)
-        if (P.damage_q[type] > 0) {
-            const int dmg = (type == 1 && cheb(ar, ac, P.flag_pos[team][0], P.flag_pos[team][1]) <= P.guardian_distance)
-                                ? P.damage_boosted_q[type] : P.damage_q[type];
+        if (HPF ? (P.damage_f[type] > 0.0) : (P.damage_q[type] > 0)) {
+            const bool boosted = type == 1 && cheb(ar, ac, P.flag_pos[team][0], P.flag_pos[team][1]) <= P.guardian_distance;
+            const int dmg = boosted ? P.damage_boosted_q[type] : P.damage_q[type];
+            const double dmgd = HPF ? (boosted ? P.damage_boosted_f[type] : P.damage_f[type]) : 0.0;
             const bool is_opp = lane < N && my_team != team && my_slot >= 0;
             const int site = 4 * a + (my_slot < 0 ? 0 : my_slot);
             const uint32_t roll = __shfl_sync(kFull, wd[0], site);
@@ -738,8 +772,9 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
             const bool hit = is_opp && (unsigned long long)roll < P.tag_threshold && d_me <= P.tagging_range;
             int hp = ag_hp(me);
             if (hit) hp -= dmg;                                                                      // (:818)
-            const bool lethal = hit && hp <= 0;                                                      // (:824)
-            if (hit) me = (me & 0xFFFFu) | ((uint32_t)(hp & 0xFFFF) << 16);
+            if (HPF && hit) hpd = __dsub_rn(hpd, dmgd);
+            const bool lethal = hit && (HPF ? (hpd <= 0.0) : (hp <= 0));                             // (:824)
+            if (!HPF && hit) me = (me & 0xFFFFu) | ((uint32_t)(hp & 0xFFFF) << 16);
             const unsigned hits = __ballot_sync(kFull, hit);
             unsigned deaths = __ballot_sync(kFull, lethal);
             moved_by_respawn = deaths != 0;
@@ -771,7 +806,10 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
                         else w.grid[P.flag_pos[1 - oteam][0] * kRow + P.flag_pos[1 - oteam][1]] = P.flag_tile[1 - oteam];
                     }
                     __syncwarp();
-                    if (lane == opp) me = pack_agent(rr, rc, 0, P.hp_max_q[P.type[opp]]);
+                    if (lane == opp) {
+                        me = pack_agent(rr, rc, 0, HPF ? 0 : P.hp_max_q[P.type[opp]]);
+                        if (HPF) hpd = P.hp_max_f[P.type[opp]];                                       // (:785)
+                    }
                 } else if (lane == 0) {
                     atomicOr(L.faults, CTF_FAULT_RESPAWN_BLOCKED);   // randint(0) raises in the reference (:771)
                 }
@@ -804,10 +842,15 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
     }
     // ---- heal_agents (:839-847)
     {
-        const int mx = P.hp_max_q[my_type];
-        int hp = ag_hp(me);
-        if (hp < mx) hp = min(hp + P.heal_q, mx);
-        me = (me & 0xFFFFu) | ((uint32_t)(hp & 0xFFFF) << 16);
+        if (HPF) {
+            const double mxd = P.hp_max_f[my_type];
+            if (hpd < mxd) hpd = fmin(__dadd_rn(hpd, P.heal_f), mxd);
+        } else {
+            const int mx = P.hp_max_q[my_type];
+            int hp = ag_hp(me);
+            if (hp < mx) hp = min(hp + P.heal_q, mx);
+            me = (me & 0xFFFFu) | ((uint32_t)(hp & 0xFFFF) << 16);
+        }
     }
     // ---- rewards (:727-730, :873, :957-966, :920-940) in fp64, stored as fp32 (ppo.py:108)
     const bool done = step >= P.game_steps;   // set at step == GAME_STEPS and never cleared until reset (:914-915)
@@ -833,7 +876,7 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
 
     // ---- write state back
     __syncwarp();
-    if (!(CTF_DIAG & 2)) store_state(P, L, w, env, me, inv, ev, lane);
+    if (!(CTF_DIAG & 2)) store_state(P, L, w, env, me, hpd, inv, ev, lane);
     if (STATS && !(CTF_DIAG & 16)) {
         if (lane < N) {   // fire-and-forget reductions: no load latency, nothing held in registers
             uint32_t* sp = L.stats + env * (long long)(CTF_N_METRICS * N) + lane;
@@ -856,13 +899,13 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
     }
 
     rev_mask_out = (L.rev_override & 0x100u) ? (L.rev_override & 0xFFu) : __ballot_sync(kFull, lane < N && P.obs_rev[li]);
-    if (!(CTF_DIAG & 4) && L.meta) write_meta(P, me, step, caps0, caps1, L.meta + env * (long long)N * P.M, lane);
+    if (!(CTF_DIAG & 4) && L.meta) write_meta<HPF>(P, me, hpd, step, caps0, caps1, L.meta + env * (long long)N * P.M, lane);
     return me;
 }
 
 // Warp-per-env step kernel: every warp steps its env and then streams that env's observation block itself.
 // The default kernel of ctf_step.
-template <typename T, bool STATS>
+template <typename T, bool STATS, bool HPF>
 __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L) {
     extern __shared__ uint4 smem_raw[];
     const uint2* lut = init_expand_lut<T>(smem_raw);
@@ -871,7 +914,7 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPl
     if (env >= L.B) return;
     const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T>, warp);
     uint32_t rev_mask;
-    const uint32_t me = step_env<STATS>(P, L, w, env, lane, rev_mask);
+    const uint32_t me = step_env<STATS, HPF>(P, L, w, env, lane, rev_mask);
     write_obs<T>(P, L, w, env, me, rev_mask, lane, lut);   // observations straight into the policy's input buffers
 }
 
@@ -913,7 +956,7 @@ struct WsCtl {
 };
 static_assert(sizeof(WsCtl) <= kWsCtlBytes, "control block");
 
-template <typename T, bool STATS>
+template <typename T, bool STATS, bool HPF>
 __global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L,
                                                      int n_logic, int n_stream, unsigned int* __restrict__ ctr) {
     extern __shared__ uint4 smem_raw[];
@@ -940,7 +983,7 @@ __global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ Dev
             if ((long long)e >= L.B) break;
             CTF_PROF_T(t1);
             uint32_t rev_mask;
-            const uint32_t me = step_env<STATS>(P, L, w, (long long)e, lane, rev_mask);
+            const uint32_t me = step_env<STATS, HPF>(P, L, w, (long long)e, lane, rev_mask);
             if (!any_obs) continue;
             CTF_PROF_T(t2);
             if (lane == 0) while (c->busy[warp]) __nanosleep(CTF_WS_SLEEP_NS);   // previous env of this warp still being streamed
@@ -1159,9 +1202,16 @@ static int build_plan(const ctf_config_t& c, int stats_level, int obs_dtype, Dev
     P.heal_q = c.heal_q; P.vault_cost_q = c.vault_cost_q; P.vault_min_q = c.vault_min_q;
     P.zone_distance = c.zone_distance; P.guardian_distance = c.guardian_distance; P.tagging_range = c.tagging_range;
     P.max_agent_blocks = c.max_agent_blocks; P.block_pickup_value = c.block_pickup_value;
+    P.hp_float = c.hp_float ? 1 : 0;
+    P.heal_f = c.heal_f; P.vault_cost_f = c.vault_cost_f; P.vault_min_f = c.vault_min_f;
     for (int t = 0; t < 4; ++t) {
-        if (c.hp_max_q[t] <= 0 || c.hp_max_q[t] > 32000) return fail(CTF_ERR_INVALID, "hp_max_q out of int16 range");
-        P.hp_max_q[t] = c.hp_max_q[t]; P.damage_q[t] = c.damage_q[t]; P.damage_boosted_q[t] = c.damage_boosted_q[t];
+        if (P.hp_float) {
+            if (!(c.hp_max_f[t] > 0.0)) return fail(CTF_ERR_INVALID, "hp_max_f must be positive");
+        } else if (c.hp_max_q[t] <= 0 || c.hp_max_q[t] > 32000) {
+            return fail(CTF_ERR_INVALID, "hp_max_q out of int16 range");
+        }
+        P.hp_max_q[t] = P.hp_float ? 1 : c.hp_max_q[t]; P.damage_q[t] = c.damage_q[t]; P.damage_boosted_q[t] = c.damage_boosted_q[t];
+        P.hp_max_f[t] = c.hp_max_f[t]; P.damage_f[t] = c.damage_f[t]; P.damage_boosted_f[t] = c.damage_boosted_f[t];
     }
     for (int i = 0; i < N; ++i) {
         if (c.agent_team[i] > 1 || c.agent_type[i] > 3) return fail(CTF_ERR_INVALID, "agent team/type out of range");
@@ -1338,9 +1388,12 @@ extern "C" int ctf_create(const ctf_config_t* cfg, int64_t num_envs, int device,
     const int ws_smem = h->ws_smem_bytes > 200 * 1024 ? (int)h->ws_smem_bytes : 200 * 1024;
 #define CTF_SET_SMEM(K, BYTES) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)
 #define CTF_SET_SMEM_T(T)                                                                                       \
-    CTF_SET_SMEM((k_step<T, false>), smem); CTF_SET_SMEM((k_step<T, true>), smem);                             \
+    CTF_SET_SMEM((k_step<T, false, false>), smem); CTF_SET_SMEM((k_step<T, true, false>), smem);               \
+    CTF_SET_SMEM((k_step<T, false, true>), smem); CTF_SET_SMEM((k_step<T, true, true>), smem);                 \
     CTF_SET_SMEM((k_reset<T, false>), smem); CTF_SET_SMEM((k_reset<T, true>), smem); CTF_SET_SMEM((k_observe<T>), smem); \
-    CTF_SET_SMEM((k_step_ws<T, false>), ws_smem); CTF_SET_SMEM((k_step_ws<T, true>), ws_smem); CTF_SET_SMEM((k_unpack<T>), smem)
+    CTF_SET_SMEM((k_step_ws<T, false, false>), ws_smem); CTF_SET_SMEM((k_step_ws<T, true, false>), ws_smem);   \
+    CTF_SET_SMEM((k_step_ws<T, false, true>), ws_smem); CTF_SET_SMEM((k_step_ws<T, true, true>), ws_smem);     \
+    CTF_SET_SMEM((k_unpack<T>), smem)
     CTF_SET_SMEM_T(float); CTF_SET_SMEM_T(uint8_t); CTF_SET_SMEM_T(__half); CTF_SET_SMEM_T(__nv_bfloat16);
 #undef CTF_SET_SMEM_T
 #undef CTF_SET_SMEM
@@ -1370,6 +1423,7 @@ extern "C" int ctf_get_sizes(ctf_handle_t h, ctf_sizes_t* s) {
     s->grid_bytes = B * kGridBytes;
     s->agents_bytes = B * P.N * 8;
     s->envs_bytes = B * 16;
+    s->hp_bytes = h->plan.hp_float ? B * P.N * sizeof(double) : 0;
     s->stats_bytes = h->stats_level > 0 ? B * CTF_N_METRICS * P.N * 4 : 0;
     s->visits_bytes = h->stats_level > 1 ? B * P.N * P.GG : 0;
     s->obs_bytes = B * P.E * elem;
@@ -1393,6 +1447,9 @@ static int make_launch(ctf_handle_t h, const ctf_state_t& st, const ctf_outputs_
     if (reinterpret_cast<uintptr_t>(out.meta) & 15) return fail(CTF_ERR_INVALID, "outputs.meta must be 16-byte aligned");
     memset(&L, 0, sizeof(L));
     L.grid = st.grid; L.agents = reinterpret_cast<unsigned long long*>(st.agents); L.envs = reinterpret_cast<uint4*>(st.envs);
+    if (h->plan.hp_float && (!st.hp || (reinterpret_cast<uintptr_t>(st.hp) & 7)))
+        return fail(CTF_ERR_INVALID, "state.hp (8-byte aligned [B][N] doubles) is required when cfg.hp_float is set");
+    L.hp = h->plan.hp_float ? st.hp : nullptr;
     L.stats = h->stats_level > 0 ? st.stats : nullptr;
     L.visits = h->stats_level > 1 ? st.visits : nullptr;
     L.obs = out.obs; L.obs_bits = out.obs_bits; L.meta = out.meta; L.rewards = out.rewards; L.dones = out.dones;
@@ -1438,16 +1495,20 @@ extern "C" int ctf_reset(ctf_handle_t h, ctf_state_t st, ctf_outputs_t out, int 
 static int launch_step(ctf_handle_t h, const Launch& L, cudaStream_t s) {
     const bool stats = h->stats_level > 0;
     const bool ws = h->B >= h->ws_min_envs;
+    const bool hpf = h->plan.hp_float != 0;
     with_obs_type(h->obs_dtype, [&](auto tag) {
         using T = decltype(tag);
-        if (ws) {
-            const unsigned threads = (unsigned)(h->ws_logic + h->ws_stream) * 32u;
-            if (stats) k_step_ws<T, true><<<h->ws_ctas, threads, h->ws_smem_bytes, s>>>(h->plan, L, h->ws_logic, h->ws_stream, h->ws_ctr);
-            else k_step_ws<T, false><<<h->ws_ctas, threads, h->ws_smem_bytes, s>>>(h->plan, L, h->ws_logic, h->ws_stream, h->ws_ctr);
-        } else {
-            if (stats) k_step<T, true><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-            else k_step<T, false><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
-        }
+        auto launch = [&](auto stats_c, auto hpf_c) {
+            constexpr bool S = decltype(stats_c)::value, F = decltype(hpf_c)::value;
+            if (ws) {
+                const unsigned threads = (unsigned)(h->ws_logic + h->ws_stream) * 32u;
+                k_step_ws<T, S, F><<<h->ws_ctas, threads, h->ws_smem_bytes, s>>>(h->plan, L, h->ws_logic, h->ws_stream, h->ws_ctr);
+            } else {
+                k_step<T, S, F><<<grid_dim(h->B), kThreads, h->smem_bytes, s>>>(h->plan, L);
+            }
+        };
+        if (stats) { if (hpf) launch(std::true_type{}, std::true_type{}); else launch(std::true_type{}, std::false_type{}); }
+        else { if (hpf) launch(std::false_type{}, std::true_type{}); else launch(std::false_type{}, std::false_type{}); }
     });
     CTF_CUDA(cudaGetLastError());
     return CTF_OK;

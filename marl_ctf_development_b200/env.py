@@ -129,6 +129,9 @@ class GridworldCtfGPU:
         self._grid = torch.zeros((B, _GRID_ROW, _GRID_ROW), dtype=torch.uint8, device=dev)
         self._agents = torch.zeros((B, N), dtype=torch.int64, device=dev)
         self._envs = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+        # HP as doubles for configurations whose HP quantities are not dyadic (cfg.hp_float); fixed point in `_agents` otherwise
+        self.hp_float = bool(ce.cfg.hp_float)
+        self._hp = torch.zeros((B, N), dtype=torch.float64, device=dev) if self.hp_float else None
         self._stats = torch.zeros((B, N_METRICS, N), dtype=torch.int32, device=dev) if self.stats_level > 0 else None
         self._visits = torch.zeros((B, N, G, G), dtype=torch.uint8, device=dev) if self.stats_level > 1 else None
         # ---- outputs (the policy's input buffers unless the caller binds its own)
@@ -156,6 +159,7 @@ class GridworldCtfGPU:
             self._grid.data_ptr(), self._agents.data_ptr(), self._envs.data_ptr(),
             self._stats.data_ptr() if self._stats is not None else None,
             self._visits.data_ptr() if self._visits is not None else None,
+            self._hp.data_ptr() if self._hp is not None else None,
         )
         self._first = True
         self.reset()
@@ -254,7 +258,7 @@ class GridworldCtfGPU:
         if a.data_ptr() != actions.data_ptr():
             raise ValueError("actions must already be a contiguous uint8 [B, N] tensor on the env's device")
         # warm-up launch outside the capture, on a snapshot so that the env does not advance
-        state = [t for t in (self._grid, self._agents, self._envs, self._stats, self._visits) if t is not None]
+        state = [t for t in (self._grid, self._agents, self._envs, self._stats, self._visits, self._hp) if t is not None]
         saved = [t.clone() for t in state]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -399,15 +403,22 @@ class GridworldCtfGPU:
             "episode": envs[:, 1].copy(),
             "captures": envs[:, 2:4].copy(),
         }
+        if self._hp is not None:
+            out["hp"] = self._hp[sel].cpu().numpy()          # agent_hp as float64 (hp_q is unused in this mode)
         if self._stats is not None:
             out["stats"] = self._stats[sel].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
         if self._visits is not None:
             out["visits"] = self._visits[sel].cpu().numpy()
         return out
 
-    def set_state(self, grid, pos, hp_q, has_flag, inventory, step, episode, captures):
-        """Inverse of get_state for the core fields (arrays with a leading B dimension)."""
+    def set_state(self, grid, pos, hp_q, has_flag, inventory, step, episode, captures, hp=None):
+        """Inverse of get_state for the core fields (arrays with a leading B dimension); ``hp`` (float64) when hp_float."""
         B, N, G = self.num_envs, self.N_AGENTS, self.GRID_SIZE
+        if self.hp_float:
+            if hp is None:
+                raise ValueError("this env keeps HP as doubles (non-dyadic HP configuration): pass hp=")
+            self._hp.copy_(torch.from_numpy(np.asarray(hp, dtype=np.float64).reshape(B, N)))
+            hp_q = np.zeros((B, N), dtype=np.int64)
         g = np.zeros((B, _GRID_ROW, _GRID_ROW), dtype=np.uint8)
         g[:, :G, :G] = np.asarray(grid, dtype=np.uint8).reshape(B, G, G)
         pos = np.asarray(pos).reshape(B, N, 2).astype(np.uint64)
@@ -573,7 +584,10 @@ class GridworldCtf:
 
     @property
     def agent_hp(self):
-        hp = self._state()["hp_q"][0]
+        st = self._state()
+        if self._gpu.hp_float:
+            return {i: float(st["hp"][0][i]) for i in range(self.N_AGENTS)}
+        hp = st["hp_q"][0]
         return {i: float(hp[i]) / self._gpu.hp_scale for i in range(self.N_AGENTS)}
 
     @property

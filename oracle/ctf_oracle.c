@@ -32,6 +32,7 @@ typedef struct ctf_oracle_env {
     uint8_t grid[CTF_MAX_CELLS];
     int32_t row[CTF_MAX_AGENTS], col[CTF_MAX_AGENTS];
     int32_t hp_q[CTF_MAX_AGENTS];
+    double hp_f[CTF_MAX_AGENTS]; /* agent_hp as Python floats when cfg->hp_float (non-dyadic HP quantities) */
     uint8_t has_flag[CTF_MAX_AGENTS];
     int32_t inventory[CTF_MAX_AGENTS];
     uint32_t stats[CTF_N_METRICS][CTF_MAX_AGENTS];
@@ -101,6 +102,7 @@ void ctf_oracle_reset(ctf_oracle_env_t* e) {
         e->col[i] = c->start_col[i];
         e->has_flag[i] = 0;                        /* :410 */
         e->hp_q[i] = c->hp_max_q[c->agent_type[i]]; /* :415 */
+        e->hp_f[i] = c->hp_max_f[c->agent_type[i]];
         e->inventory[i] = 0;                       /* :418 */
     }
     e->caps[0] = e->caps[1] = 0;
@@ -144,6 +146,7 @@ static void respawn(ctf_oracle_env_t* e, int agent, uint32_t word) {
         int old_r = e->row[agent], old_c = e->col[agent];
         e->row[agent] = nr; e->col[agent] = nc;             /* :782 */
         e->hp_q[agent] = c->hp_max_q[c->agent_type[agent]]; /* :785 */
+        e->hp_f[agent] = c->hp_max_f[c->agent_type[agent]];
         if (e->has_flag[agent] == 1) {                      /* :788-794 */
             e->has_flag[agent] = 0;
             if (c->drop_flag_when_no_hp)
@@ -196,9 +199,14 @@ static double act(ctf_oracle_env_t* e, int agent, int action) {
     if (nr >= 0 && nr < G && nc >= 0 && nc < G) {                    /* is_valid_move :636-641 */
         const int target = CELL(e, nr, nc);
         /* move_to_open_tile (:643-650) */
-        if (target == 0 && (action <= 3 || (action >= 5 && type == 2 && (e->hp_q[agent] - c->vault_cost_q) > c->vault_min_q))) {
+        const int can_vault = c->hp_float ? ((e->hp_f[agent] - c->vault_cost_f) > c->vault_min_f)   /* :648-650, Python floats */
+                                          : ((e->hp_q[agent] - c->vault_cost_q) > c->vault_min_q);
+        if (target == 0 && (action <= 3 || (action >= 5 && type == 2 && can_vault))) {
             movement_handler(e, agent, nr, nc);
-            if (action >= 5 && type == 2) e->hp_q[agent] -= c->vault_cost_q; /* update_vaulter_hp :652-657 */
+            if (action >= 5 && type == 2) {                                   /* update_vaulter_hp :652-657 */
+                e->hp_q[agent] -= c->vault_cost_q;
+                e->hp_f[agent] -= c->vault_cost_f;
+            }
         }
         /* can_add_blocks (:659-667) -> add_block (:614-634) */
         else if (action >= 5 && type == 3 && e->inventory[agent] > 0 && target == 0 &&
@@ -236,10 +244,13 @@ static double tagging_logic(ctf_oracle_env_t* e, int agent) {
     const ctf_config_t* c = e->cfg;
     const int type = c->agent_type[agent], team = c->agent_team[agent];
     double tagging_reward = 0;
-    if (c->damage_q[type] > 0) {                     /* :804 */
+    if (c->hp_float ? (c->damage_f[type] > 0.0) : (c->damage_q[type] > 0)) {   /* :804 */
         int dmg = c->damage_q[type];
-        if (cheb(e->row[agent], e->col[agent], c->flag_pos[team][0], c->flag_pos[team][1]) <= c->guardian_distance && type == 1)
+        double dmg_f = c->damage_f[type];
+        if (cheb(e->row[agent], e->col[agent], c->flag_pos[team][0], c->flag_pos[team][1]) <= c->guardian_distance && type == 1) {
             dmg = c->damage_boosted_q[type];         /* :808-810, :818 */
+            dmg_f = c->damage_boosted_f[type];
+        }
         for (int j = 0; j < c->n_opponents[team]; ++j) { /* :813, OPPONENTS in id order */
             const int opp = c->opponents[team][j];
             const uint32_t* w = e->words[4 * agent + j];
@@ -247,8 +258,9 @@ static double tagging_logic(ctf_oracle_env_t* e, int agent) {
             if ((uint64_t)w[0] < c->tag_threshold &&
                 cheb(e->row[agent], e->col[agent], e->row[opp], e->col[opp]) <= c->tagging_range) {
                 e->hp_q[opp] -= dmg;                 /* :818 */
+                e->hp_f[opp] -= dmg_f;
                 bump(e, CTF_M_TAG_COUNT, agent, 1);
-                if (e->hp_q[opp] <= 0) {             /* :824 */
+                if (c->hp_float ? (e->hp_f[opp] <= 0.0) : (e->hp_q[opp] <= 0)) {   /* :824 */
                     if (e->has_flag[opp] == 1) bump(e, CTF_M_FLAG_DISPOSSESSIONS, agent, 1);
                     respawn(e, opp, w[1]);           /* :831 */
                     tagging_reward = c->reward_tag;  /* :832 */
@@ -304,6 +316,8 @@ void ctf_oracle_step(ctf_oracle_env_t* e, const uint8_t* actions, float* rewards
     for (int i = 0; i < N; ++i) {
         int mx = c->hp_max_q[c->agent_type[i]];
         if (e->hp_q[i] < mx) e->hp_q[i] = imin(e->hp_q[i] + c->heal_q, mx);
+        const double mx_f = c->hp_max_f[c->agent_type[i]];                  /* :845-846 with Python floats */
+        if (e->hp_f[i] < mx_f) { e->hp_f[i] += c->heal_f; if (!(e->hp_f[i] <= mx_f)) e->hp_f[i] = mx_f; }
     }
     /* get_adjusted_rewards (:957-966) */
     if (c->use_adjusted_rewards)
@@ -411,7 +425,9 @@ void ctf_oracle_metadata(const ctf_oracle_env_t* e, int agent, float* out /* [6+
     m[0] = (double)e->step / (double)c->game_steps;                         /* :1035 */
     m[1] = (double)(e->caps[team] + 1) / (double)(e->caps[1 - team] + 1);   /* :1036 */
     /* :1039-1041 — HP of the agent whose *id* equals agent i's type, over agent i's max HP, as uint8 */
-    for (int i = 0; i < N; ++i) hp8[i] = (uint8_t)(e->hp_q[c->meta_hp_src[i]] / c->hp_max_q[c->agent_type[i]]);
+    for (int i = 0; i < N; ++i)
+        hp8[i] = c->hp_float ? (uint8_t)((int)(e->hp_f[c->meta_hp_src[i]] / c->hp_max_f[c->agent_type[i]]) & 0xFF)
+                             : (uint8_t)(e->hp_q[c->meta_hp_src[i]] / c->hp_max_q[c->agent_type[i]]);
     m[2 + c->agent_type[agent]] = 1.0;                                      /* :1047 */
     m[6] = hp8[agent];                                                      /* :1050 */
     m[7] = e->has_flag[agent];                                              /* :1051 */
@@ -608,6 +624,18 @@ void ctf_oracle_batch_destroy(ctf_oracle_batch_t* bt) {
     free(bt->envs);
     free(bt);
 }
+
+void ctf_oracle_batch_get_hp_f(const ctf_oracle_batch_t* bt, double* out) {
+    for (int b = 0; b < bt->B; ++b)
+        for (int i = 0; i < bt->cfg.n_agents; ++i) out[b * bt->cfg.n_agents + i] = bt->envs[b].hp_f[i];
+}
+
+void ctf_oracle_batch_set_hp_f(ctf_oracle_batch_t* bt, const double* in) {
+    for (int b = 0; b < bt->B; ++b)
+        for (int i = 0; i < bt->cfg.n_agents; ++i) bt->envs[b].hp_f[i] = in[b * bt->cfg.n_agents + i];
+}
+
+void ctf_oracle_get_hp_f(const ctf_oracle_env_t* e, double* out) { for (int i = 0; i < e->cfg->n_agents; ++i) out[i] = e->hp_f[i]; }
 
 uint32_t ctf_oracle_take_faults(ctf_oracle_env_t* e) { uint32_t f = e->faults; e->faults = 0; return f; }
 

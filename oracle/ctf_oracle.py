@@ -62,6 +62,9 @@ def lib():
         L.ctf_oracle_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int]
         L.ctf_oracle_batch_run.restype = C.c_double
         L.ctf_oracle_observe_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ctf_oracle_get_hp_f.argtypes = [C.c_void_p, C.c_void_p]
+        L.ctf_oracle_batch_get_hp_f.argtypes = [C.c_void_p, C.c_void_p]
+        L.ctf_oracle_batch_set_hp_f.argtypes = [C.c_void_p, C.c_void_p]
         L.ctf_oracle_take_faults.argtypes = [C.c_void_p]
         L.ctf_oracle_take_faults.restype = C.c_uint32
         L.ctf_oracle_batch_take_faults.argtypes = [C.c_void_p]
@@ -136,10 +139,13 @@ class OracleEnv:
         stats = np.zeros((N_METRICS, n), dtype=np.uint32)
         visits = np.zeros((n, g, g), dtype=np.uint8)
         self.L.ctf_oracle_get_state(self._e, _p(grid), _p(pos), _p(hp), _p(flag), _p(inv), _p(sc), _p(stats), _p(visits))
+        hp_f = np.zeros(n, dtype=np.float64)
+        self.L.ctf_oracle_get_hp_f(self._e, _p(hp_f))
         return {
             "grid": grid,
             "pos": pos.astype(np.uint8),
             "hp_q": hp,
+            "hp": hp_f,     # agent_hp as floats (what is compared when cfg.hp_float; hp_q / hp_scale otherwise)
             "has_flag": flag,
             "inventory": inv,
             "step": int(sc[0]),
@@ -218,10 +224,13 @@ class OracleBatch:
         stats = np.zeros((B, N_METRICS, n), dtype=np.uint32)
         visits = np.zeros((B, n, g, g), dtype=np.uint8)
         self.L.ctf_oracle_batch_get_state(self._h, _p(grid), _p(pos), _p(hp), _p(flag), _p(inv), _p(sc), _p(stats), _p(visits))
+        hp_f = np.zeros((B, n), dtype=np.float64)
+        self.L.ctf_oracle_batch_get_hp_f(self._h, _p(hp_f))
         return {
             "grid": grid,
             "pos": pos.astype(np.uint8),
             "hp_q": hp,
+            "hp": hp_f,
             "has_flag": flag,
             "inventory": inv,
             "step": sc[:, 0].astype(np.int64),
@@ -232,8 +241,10 @@ class OracleBatch:
             "visits": visits,
         }
 
-    def set_state(self, grid, pos, hp_q, has_flag, inventory, step, episode, captures):
+    def set_state(self, grid, pos, hp_q, has_flag, inventory, step, episode, captures, hp=None):
         B = self.B
+        if hp is not None:   # float HP (cfg.hp_float)
+            self.L.ctf_oracle_batch_set_hp_f(self._h, _p(np.ascontiguousarray(np.asarray(hp, dtype=np.float64).reshape(B, self.N))))
         grid = np.ascontiguousarray(np.asarray(grid, dtype=np.uint8))
         pos = np.ascontiguousarray(np.asarray(pos, dtype=np.int32))
         hp = np.ascontiguousarray(np.asarray(hp_q, dtype=np.int32))

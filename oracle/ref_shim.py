@@ -379,11 +379,12 @@ def snapshot(env, hp_scale: int) -> dict:
     pos = np.array([env.agent_positions[i] for i in range(n)], dtype=np.uint8)
     hp = np.array([int(round(env.agent_hp[i] * hp_scale)) for i in range(n)], dtype=np.int32)
     for i in range(n):
-        assert hp[i] == env.agent_hp[i] * hp_scale, "HP not exact in fixed point"
+        assert hp_scale == 0 or hp[i] == env.agent_hp[i] * hp_scale, "HP not exact in fixed point"
     return {
         "grid": env.grid.astype(np.uint8).copy(),
         "pos": pos,
         "hp_q": hp,
+        "hp": np.array([float(env.agent_hp[i]) for i in range(n)], dtype=np.float64),   # compared bit for bit when cfg.hp_float
         "has_flag": env.has_flag.astype(np.uint8).copy(),
         "inventory": np.array([env.block_inventory[i] for i in range(n)], dtype=np.int32),
         "step": int(env.env_step_count),

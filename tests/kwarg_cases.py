@@ -35,6 +35,16 @@ KWARG_CASES = [
                                             "AGENT_TYPE_DAMAGE": {0: 0.5, 1: 0.25, 2: 0.5, 3: 0.5}, "GUARDIAN_DAMAGE_MULTIPLIER": 2.0}, "seek"),
     ("glass_cannons_gridlocked", "7_gridlocked", {"TAG_PROBABILITY": 0.9, "AGENT_TYPE_HP": {0: 1.5, 1: 1, 2: 2, 3: 1},
                                                   "AGENT_TYPE_DAMAGE": {0: 1, 1: 0.5, 2: 1, 3: 2}, "AGENT_HP_HEALING_PER_STEP": 0.5}, "builder"),
+    # HP quantities that are not dyadic rationals: the backend switches to IEEE-double HP (cfg.hp_float) and has to follow the
+    # reference's Python float arithmetic operation by operation (0.1 + 0.1 + 0.1 != 0.3)
+    ("float_hp_heal_tenth", "8_arena", {"AGENT_HP_HEALING_PER_STEP": 0.1}, "seek"),
+    ("float_hp_everything", "8_arena", {"AGENT_HP_HEALING_PER_STEP": 0.1, "AGENT_TYPE_DAMAGE": {0: 0.3, 1: 0.7, 2: 0.9, 3: 0.35},
+                                        "VAULT_HP_COST": 0.45, "VAULT_MIN_HP": 1.1, "AGENT_TYPE_HP": {0: 3.3, 1: 2.9, 2: 4.1, 3: 2.2},
+                                        "GUARDIAN_DAMAGE_MULTIPLIER": 2.7}, "seek"),
+    ("float_hp_gridlocked_builder", "7_gridlocked", {"AGENT_TYPE_DAMAGE": {0: 0.3, 1: 0.2, 2: 0.6, 3: 0.7}, "VAULT_HP_COST": 0.3,
+                                                     "VAULT_MIN_HP": 0.7, "AGENT_HP_HEALING_PER_STEP": 0.05}, "builder"),
+    ("float_hp_one_hit_kills", "0_the_split", {"TAG_PROBABILITY": 1.0, "AGENT_TYPE_HP": {0: 0.3, 1: 0.3, 2: 0.3, 3: 0.3},
+                                               "AGENT_TYPE_DAMAGE": {0: 0.3, 1: 0.1, 2: 0.3, 3: 0.3}, "GUARDIAN_DAMAGE_MULTIPLIER": 3.0}, "seek"),
 ]
 
 CASE_IDS = [c[0] for c in KWARG_CASES]

@@ -101,10 +101,22 @@ def test_rejects_what_the_reference_cannot_run():
     with pytest.raises(KeyError):
         compile_config(**{**ec, "AGENT_CONFIG": two})  # get_env_metadata reads agent_hp[3] (gridworld_ctf.py:1041)
     with pytest.raises(ValueError):
-        compile_config(**{**ec, "AGENT_HP_HEALING_PER_STEP": 0.1})  # not a dyadic rational
+        compile_config(**{**ec, "AGENT_TYPE_HP": {0: 8, 1: 0, 2: 4, 3: 4}})  # an agent type without HP
     shuffled = {1: {"team": 1, "type": 0}, 0: {"team": 0, "type": 0}}
     with pytest.raises(ValueError):
         compile_config(**{**ec, "AGENT_CONFIG": shuffled})  # insertion order matters in the reference
+
+
+def test_non_dyadic_hp_quantities_switch_to_float_hp():
+    """Quantities that are not dyadic rationals (heal 0.1) cannot live in exact fixed point: HP becomes IEEE doubles and the
+    device performs the reference's float operations one by one (cfg.hp_float); every shipped config stays fixed point."""
+    ec = experiment_env_config("8_arena")
+    assert compile_config(**ec).cfg.hp_float == 0 and compile_config(**ec).cfg.hp_scale == 4
+    ce = compile_config(**{**ec, "AGENT_HP_HEALING_PER_STEP": 0.1})
+    assert ce.cfg.hp_float == 1 and ce.cfg.hp_scale == 0 and ce.cfg.heal_f == 0.1
+    assert list(ce.cfg.hp_max_f) == [10.0, 8.0, 8.0, 7.0]
+    ce = compile_config(**{**ec, "AGENT_TYPE_DAMAGE": {0: 0.3, 1: 0.7, 2: 1, 3: 1}, "GUARDIAN_DAMAGE_MULTIPLIER": 2.7})
+    assert ce.cfg.hp_float == 1 and ce.cfg.damage_boosted_f[1] == 0.7 * 2.7    # one float multiplication, like :818
 
 
 def test_default_hp_configs_compile():

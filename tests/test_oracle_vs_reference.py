@@ -123,7 +123,7 @@ def test_constructor_keyword_variations(name, exp, overrides, kind):
         a = pol(rng, s["pos"], s["has_flag"])
         _, rr, rd = ref.step(a.tolist())
         orr, od = orc.step(a)
-        assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"{name} t={t}")
+        assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"{name} t={t}", float_hp=bool(ce.cfg.hp_float))
         assert rd == od
         assert np.array_equal(bits(np.array(rr, dtype=np.float32)), bits(orr)), (name, t, rr, orr)
         if t % 7 == 0 or t == steps - 1:
