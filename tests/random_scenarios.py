@@ -15,14 +15,32 @@ class _Retry(Exception):
     pass
 
 
+DECIMAL_HP_SEEDS = tuple(range(100, 108))   # seeds whose HP tables are decimals (tenths / twentieths): IEEE-double HP mode
+
+
 def random_env_config(seed: int) -> dict:
-    """Deterministic in ``seed``; internally re-draws when a placement cannot be completed."""
+    """Deterministic in ``seed``; internally re-draws when a placement cannot be completed.  Seeds in DECIMAL_HP_SEEDS get
+    HP / damage / heal / vault quantities that are not dyadic rationals (0.3, 1.15, ...), which no fixed point holds exactly."""
     for attempt in range(1000):
         try:
-            return _draw(np.random.default_rng([seed, attempt]))
+            ec = _draw(np.random.default_rng([seed, attempt]))
+            break
         except _Retry:
             continue
-    raise RuntimeError("no valid scenario found")
+    else:
+        raise RuntimeError("no valid scenario found")
+    if seed in DECIMAL_HP_SEEDS:
+        rng = np.random.default_rng([seed, 12345])
+        d = lambda lo, hi: float(rng.integers(lo, hi)) / 20.0  # noqa: E731
+        ec.update({
+            "AGENT_TYPE_HP": {t: d(11, 120) for t in range(4)},
+            "AGENT_TYPE_DAMAGE": {t: d(0, 45) for t in range(4)},
+            "AGENT_HP_HEALING_PER_STEP": d(0, 12),
+            "GUARDIAN_DAMAGE_MULTIPLIER": float(rng.choice([1.0, 1.7, 2.3, 5.0])),
+            "VAULT_HP_COST": d(0, 40),
+            "VAULT_MIN_HP": d(0, 60),
+        })
+    return ec
 
 
 def _draw(rng) -> dict:

@@ -174,7 +174,7 @@ def test_constructor_keyword_variations(name, exp, overrides, kind):
     _run_against_oracle(exp, 96, steps, kind, seed=23, obs_every=15, stats="full", env_overrides=dict(overrides))
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", list(range(24)) + list(range(100, 108)))
 def test_random_scenarios_and_configs(seed):
     """The random maps / team layouts / HP tables pinned against the reference in test_oracle_vs_reference.py."""
     from marl_ctf_development_b200 import GridworldCtfGPU

@@ -137,7 +137,7 @@ def test_constructor_keyword_variations(name, exp, overrides, kind):
     assert np.array_equal(vm, st["visits"])
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", list(range(24)) + list(range(100, 108)))
 def test_random_scenarios_and_configs(seed):
     """Random maps (grid 6..16, any FLIP_AXIS), team layouts, HP tables: reference == oracle step by step."""
     from random_scenarios import random_env_config
@@ -155,7 +155,7 @@ def test_random_scenarios_and_configs(seed):
         a = pol(rng, s["pos"], s["has_flag"])
         _, rr, rd = ref.step(a.tolist())
         orr, od = orc.step(a)
-        assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"seed {seed} t={t}")
+        assert_state_equal(orc.state(), rs.snapshot(ref, ce.cfg.hp_scale), f"seed {seed} t={t}", float_hp=bool(ce.cfg.hp_float))
         assert rd == od
         assert np.array_equal(bits(np.array(rr, dtype=np.float32)), bits(orr)), (seed, t, rr, orr)
         if t % 5 == 0:
