@@ -71,6 +71,18 @@ class GridworldCtfGPU:
         self._lib = _native.load()  # raises when the extension is missing
         if not torch.cuda.is_available():
             raise _native.NativeError("GridworldCtfGPU needs a CUDA device (sm_100a); there is no CPU fallback")
+        # what pickling / copy.deepcopy rebuild the env from (Ray ships pickled env copies: league_training.py:686-687)
+        self._ctor = dict(
+            AGENT_CONFIG=AGENT_CONFIG, SCENARIO=SCENARIO, GAME_STEPS=GAME_STEPS, GRID_SIZE=GRID_SIZE,
+            ENABLE_OBSTACLES=ENABLE_OBSTACLES, DROP_FLAG_WHEN_NO_HP=DROP_FLAG_WHEN_NO_HP, HOME_FLAG_CAPTURE=HOME_FLAG_CAPTURE,
+            USE_EASY_CAPTURE=USE_EASY_CAPTURE, USE_ADJUSTED_REWARDS=USE_ADJUSTED_REWARDS, MAX_BLOCK_TILE_PCT=MAX_BLOCK_TILE_PCT,
+            LOG_METRICS=LOG_METRICS, MAP_SYMMETRY_CHECK=MAP_SYMMETRY_CHECK, AGENT_TYPE_HP=AGENT_TYPE_HP,
+            AGENT_HP_HEALING_PER_STEP=AGENT_HP_HEALING_PER_STEP, AGENT_TYPE_DAMAGE=AGENT_TYPE_DAMAGE,
+            TAG_PROBABILITY=TAG_PROBABILITY, GUARDIAN_DAMAGE_MULTIPLIER=GUARDIAN_DAMAGE_MULTIPLIER, VAULT_HP_COST=VAULT_HP_COST,
+            VAULT_MIN_HP=VAULT_MIN_HP, num_envs=num_envs, device=None if device is None else str(device), seed=seed,
+            env_id_base=env_id_base, stats=stats, obs_dtype=obs_dtype, reverse_team1_actions=reverse_team1_actions,
+            validate_actions=validate_actions, packed_obs=packed_obs, dense_obs=dense_obs,
+        )
         self.ce = compile_config(
             AGENT_CONFIG=AGENT_CONFIG, SCENARIO=SCENARIO, GAME_STEPS=GAME_STEPS, GRID_SIZE=GRID_SIZE,
             ENABLE_OBSTACLES=ENABLE_OBSTACLES, DROP_FLAG_WHEN_NO_HP=DROP_FLAG_WHEN_NO_HP,
@@ -207,6 +219,31 @@ class GridworldCtfGPU:
         if meta is not None:
             self._check_out(meta, (B, N, M), torch.float32, "meta")
             self.meta = meta
+
+    # ------------------------------------------------------------------ pickling (Ray object store, copy.deepcopy)
+    def __getstate__(self):
+        """Constructor arguments + the decoded device state; the copy owns a new handle and new buffers (caller-bound
+        output buffers are not carried over).  Synchronises."""
+        return {"ctor": dict(self._ctor), "state": self.get_state(), "first": self._first}
+
+    def __setstate__(self, d):
+        ctor = dict(d["ctor"])
+        ctor["MAP_SYMMETRY_CHECK"] = False                       # already checked when the original was built
+        self.__init__(**ctor)
+        self._ctor["MAP_SYMMETRY_CHECK"] = d["ctor"]["MAP_SYMMETRY_CHECK"]
+        self.MAP_SYMMETRY_CHECK = d["ctor"]["MAP_SYMMETRY_CHECK"]
+        st = d["state"]
+        self.set_state(st["grid"], st["pos"], st["hp_q"], st["has_flag"], st["inventory"], st["step"], st["episode"], st["captures"],
+                       hp=st.get("hp"))
+        if self._stats is not None:
+            self._stats.copy_(torch.from_numpy(st["stats"].astype(np.int32)))
+        if self._visits is not None:
+            self._visits.copy_(torch.from_numpy(st["visits"]))
+        self._first = d["first"]
+        # observations / metadata of the restored state; rewards and dones are those of the next step
+        out = self._outputs(rewards=False, dones=False)
+        _native.check(self._lib.ctf_observe(self._handle, self._state_struct, None, out, self._stream()))
+        self.dones.copy_((self._envs[:, 0] >= self.GAME_STEPS).to(torch.uint8))
 
     def close(self):
         if getattr(self, "_handle", None) is not None:
@@ -404,7 +441,8 @@ class GridworldCtfGPU:
             "captures": envs[:, 2:4].copy(),
         }
         if self._hp is not None:
-            out["hp"] = self._hp[sel].cpu().numpy()          # agent_hp as float64 (hp_q is unused in this mode)
+            out["hp"] = self._hp[sel].cpu().numpy()          # agent_hp as float64
+            out["hp_q"] = np.zeros_like(out["hp_q"])          # the record's HP field is a don't-care in this mode
         if self._stats is not None:
             out["stats"] = self._stats[sel].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
         if self._visits is not None:
@@ -501,6 +539,14 @@ def metrics_dict(ce, counters, visits=None) -> dict:
     return m
 
 
+_VIEW_ATTRS = (
+    "N_AGENTS", "GRID_SIZE", "GAME_STEPS", "FLIP_AXIS", "AGENT_CONFIG", "SCENARIO", "AGENT_TEAMS", "AGENT_TYPES",
+    "AGENT_TILE_MAP", "AGENT_TYPE_ACTION_MASK", "AGENT_TYPE_HP", "AGENT_TYPE_DAMAGE", "OPPONENTS", "TILES_USED",
+    "FLAG_POSITIONS", "CAPTURE_POSITIONS", "SPAWN_POSITIONS", "AGENT_STARTING_POSITIONS", "SCENARIO_NAME",
+    "ACTION_SPACE", "REVERSED_ACTION_MAP",
+)
+
+
 class GridworldCtf:
     """Single-env view with the reference's exact surface (gridworld_ctf.py), backed by one GPU env.
 
@@ -514,13 +560,17 @@ class GridworldCtf:
             *args, num_envs=1, device=device, seed=seed, env_id_base=env_id, stats="full", obs_dtype=torch.uint8, **kwargs
         )
         g = self._gpu
-        for name in (
-            "N_AGENTS", "GRID_SIZE", "GAME_STEPS", "FLIP_AXIS", "AGENT_CONFIG", "SCENARIO", "AGENT_TEAMS", "AGENT_TYPES",
-            "AGENT_TILE_MAP", "AGENT_TYPE_ACTION_MASK", "AGENT_TYPE_HP", "AGENT_TYPE_DAMAGE", "OPPONENTS", "TILES_USED",
-            "FLAG_POSITIONS", "CAPTURE_POSITIONS", "SPAWN_POSITIONS", "AGENT_STARTING_POSITIONS", "SCENARIO_NAME",
-            "ACTION_SPACE", "REVERSED_ACTION_MAP",
-        ):
+        for name in _VIEW_ATTRS:
             setattr(self, name, getattr(g, name))
+        self._cache = {}
+
+    def __getstate__(self):
+        return {"gpu": self._gpu}
+
+    def __setstate__(self, d):
+        self._gpu = d["gpu"]
+        for name in _VIEW_ATTRS:
+            setattr(self, name, getattr(self._gpu, name))
         self._cache = {}
 
     # -- reference methods

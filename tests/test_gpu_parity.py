@@ -756,3 +756,50 @@ def test_get_state_of_selected_envs_and_current_device_is_preserved():
             assert torch.cuda.current_device() == 1
             assert torch.empty(1, device="cuda").device.index == 1
     assert torch.cuda.current_device() == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# pickling / deepcopy: Ray ships pickled env copies to its workers (league_training.py:686-687)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("overrides", [{}, {"AGENT_HP_HEALING_PER_STEP": 0.1, "AGENT_TYPE_DAMAGE": {0: 0.3, 1: 0.7, 2: 0.9, 3: 0.35}}],
+                         ids=["fixed_point_hp", "float_hp"])
+def test_env_pickles_mid_episode_and_the_copy_continues_identically(overrides):
+    import copy
+    import pickle
+
+    env = _env("7_gridlocked", 40, seed=9, env_id_base=300, stats="full", packed_obs=True, env_overrides=overrides)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    acts = torch.randint(0, 9, (60, 40, env.N_AGENTS), dtype=torch.uint8, device="cuda", generator=gen)
+    for t in range(25):
+        env.step(acts[t])
+    clone = pickle.loads(pickle.dumps(env))
+    assert clone._handle.value != env._handle.value and clone.obs.data_ptr() != env.obs.data_ptr()
+    assert torch.equal(clone.obs, env.obs) and torch.equal(clone.meta, env.meta) and torch.equal(clone.obs_bits, env.obs_bits)
+    twin = copy.deepcopy(clone)
+    for t in range(25, 60):
+        a, b, c = env.step(acts[t]), clone.step(acts[t]), twin.step(acts[t])
+        for x, y, z in zip(a[:4], b[:4], c[:4]):
+            assert torch.equal(x, y) and torch.equal(x, z), t
+    s0, s1 = env.get_state(), twin.get_state()
+    for k in s0:
+        assert np.array_equal(s0[k], s1[k]), k
+
+
+def test_single_env_view_deepcopies_like_the_reference_env():
+    import copy
+
+    from marl_ctf_development_b200 import GridworldCtf
+
+    env = GridworldCtf(**experiment_env_config("8_arena"), seed=2, env_id=5)
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        env.step(rng.integers(0, 9, 8).tolist())
+    other = copy.deepcopy(env)
+    assert other.env_step_count == 12 and other.agent_positions == env.agent_positions
+    for _ in range(20):
+        a = rng.integers(0, 9, 8).tolist()
+        g0, r0, d0 = env.step(a)
+        g1, r1, d1 = other.step(a)
+        assert np.array_equal(g0, g1) and r0 == r1 and d0 == d1
+    assert np.array_equal(env.standardise_state(3, reverse_grid=True), other.standardise_state(3, reverse_grid=True))
+    assert env.metrics["agent_tag_count"] == other.metrics["agent_tag_count"]
