@@ -1061,7 +1061,10 @@ __global__ void __launch_bounds__(1024, 1) k_step_ws(const __grid_constant__ Dev
 // The chunk's packed words (wpa per block, coalesced) are re-packed in shared memory into ONE contiguous bit string
 // (block b's nbits elements follow block b-1's directly, shifted by the output's alignment pad) and all warps stream
 // the chunk's output region together — CTAs are scheduled in address order, so few blocks are open at a time.
-constexpr int kUnpackThreads = 256;
+#ifndef CTF_UNPACK_THREADS
+#define CTF_UNPACK_THREADS 256   // 512 measured too: profiles/r02_unpack_threads.log
+#endif
+constexpr int kUnpackThreads = CTF_UNPACK_THREADS;
 template <typename T>
 __global__ void __launch_bounds__(kUnpackThreads) k_unpack(const uint32_t* __restrict__ packed, T* __restrict__ out,
                                                           long long n_blocks, int nbits, int wpa, int chunk, int bits_words) {
