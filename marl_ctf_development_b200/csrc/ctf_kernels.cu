@@ -446,6 +446,9 @@ __device__ __forceinline__ void write_obs(const DevPlan& P, const Launch& L, con
     if (out) stream_env<T>(w.bits, P.E, out, 0, 1, lane, lut);
 }
 
+#ifndef CTF_COOP_STREAM
+#define CTF_COOP_STREAM 1   // k_step: 1 = the CTA's warps stream its env blocks together (below), 0 = every warp streams its own
+#endif
 #ifndef CTF_META_VEC
 #define CTF_META_VEC 1   // 1: whole [N][M] block as float4 stores; 0: one 4-byte store per element
 #endif
@@ -903,19 +906,48 @@ __device__ __forceinline__ uint32_t step_env(const DevPlan& P, const Launch& L, 
     return me;
 }
 
-// Warp-per-env step kernel: every warp steps its env and then streams that env's observation block itself.
-// The default kernel of ctf_step.
+// Warp-per-env step kernel, the default kernel of ctf_step: every warp steps its env and builds that env's observation
+// bit string in its own shared-memory buffer; after one barrier the CTA's warps write the CTA's kWarpsPerCta consecutive
+// env blocks one after the other, all warps on the same block (2 KB contiguous per pass) — a quarter as many open
+// write streams as when every warp streams its own block, and each CTA's region goes out in address order.
+// profiles/r02_coop_stream.log: 8_arena float32 0.980 -> 0.974 ms, uint8 0.283 -> 0.281, 7_gridlocked B = 16384 0.1475 -> 0.1450;
+// 4 warps x 5 resident CTAs and 2 x 9 tie, 8 x 3 (0.987) and 16 x 1 (1.18) lose: the barrier idles too much of the SM.
+// Per-env ready flags instead of the barrier (a block is written by whichever warps are ready) are SLOWER, 0.9825 vs 0.9786 ms,
+// uint8 0.295 vs 0.2835 (profiles/r02_coop_flag.log): the aligned passes are what helps.
 template <typename T, bool STATS, bool HPF>
 __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevPlan P, const __grid_constant__ Launch L) {
     extern __shared__ uint4 smem_raw[];
     const uint2* lut = init_expand_lut<T>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long env = (long long)blockIdx.x * kWarpsPerCta + warp;
+#if CTF_COOP_STREAM
+    unsigned char* base = reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T>;
+    if (env < L.B) {
+        const WarpMem w = warp_mem(P, base, warp);
+        uint32_t rev_mask;
+        const uint32_t me = step_env<STATS, HPF>(P, L, w, env, lane, rev_mask);
+        if (L.obs || L.obs_bits) {
+            T* out = L.obs ? reinterpret_cast<T*>(L.obs) + env * (long long)P.E : nullptr;
+            const int pad = out ? obs_pad(out) : 0;
+            build_obs_bits(P, w, me, rev_mask, pad, lane);
+            if (L.obs_bits) store_packed(P, w.bits, pad, L.obs_bits + env * (long long)(P.N * P.wpa), 0, 1, lane);
+        }
+    }
+    __syncthreads();
+    if (L.obs) {
+        for (int e = 0; e < kWarpsPerCta; ++e) {
+            const long long env_e = (long long)blockIdx.x * kWarpsPerCta + e;
+            if (env_e >= L.B) break;
+            stream_env<T>(warp_mem(P, base, e).bits, P.E, reinterpret_cast<T*>(L.obs) + env_e * (long long)P.E, warp, kWarpsPerCta, lane, lut);
+        }
+    }
+#else
     if (env >= L.B) return;
     const WarpMem w = warp_mem(P, reinterpret_cast<unsigned char*>(smem_raw) + kLutBytes<T>, warp);
     uint32_t rev_mask;
     const uint32_t me = step_env<STATS, HPF>(P, L, w, env, lane, rev_mask);
     write_obs<T>(P, L, w, env, me, rev_mask, lane, lut);   // observations straight into the policy's input buffers
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
